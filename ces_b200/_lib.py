@@ -1,0 +1,97 @@
+"""ctypes binding of libces_b200.so (include/ces_b200.h).
+
+The library is the product: if it is missing or fails to load this module raises
+-- there is no CPU fallback anywhere in ces_b200.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libces_b200.so")
+
+CES_OK = 0
+CES_ERR_INVALID, CES_ERR_STATE, CES_ERR_ALIGN, CES_ERR_NOT_SPD, CES_ERR_CUDA, CES_ERR_NOMEM = -1, -2, -3, -4, -5, -6
+RULES = {"eks": 0, "aldi": 1, "aldi_constant": 2, "eki": 3}
+TS_FROBENIUS, TS_FIXED = 0, 1
+MAPS = {"lineal": 0, "lineal_log": 1, "elliptic": 2, "banana": 3}
+
+# every symbol include/ces_b200.h declares (tests/test_abi.py checks the .so exports them all)
+EXPORTS = (
+    "ces_version", "ces_last_error", "ces_create", "ces_destroy", "ces_set_problem", "ces_phase1_sums",
+    "ces_phase2_centre", "ces_phase3_interact", "ces_phase4a_drift", "ces_phase4_update", "ces_step",
+    "ces_step_host", "ces_forward_map", "ces_buffer", "ces_launch_count", "ces_gemm", "ces_potrf", "ces_posv",
+)
+
+_i64, _int, _dbl, _vp = ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_void_p
+_dp = ctypes.c_void_p  # double* (host or device) passed as an address
+
+
+class CesError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("ces_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Load libces_b200.so (once).  Raises OSError with build instructions if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise OSError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                      "(or `make -C ces_b200/csrc`).  ces_b200 has no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.ces_version.restype = ctypes.c_char_p
+    lib.ces_last_error.restype = ctypes.c_char_p
+    lib.ces_launch_count.restype = _i64
+    lib.ces_launch_count.argtypes = [_vp]
+    lib.ces_create.argtypes = [_i64, _i64, _i64, _i64, _int, _int, _i64, _vp, _i64, ctypes.POINTER(_vp)]
+    lib.ces_destroy.argtypes = [_vp]
+    lib.ces_set_problem.argtypes = [_vp, _dp, _dp, _dp, _dp, _dp]
+    lib.ces_phase1_sums.argtypes = [_vp, _dp, _i64, _dp, _i64]
+    lib.ces_phase2_centre.argtypes = [_vp, _int, _dp, _i64, _dp, _i64]
+    lib.ces_phase3_interact.argtypes = [_vp, _int]
+    lib.ces_phase4a_drift.argtypes = [_vp, _dbl]
+    lib.ces_phase4_update.argtypes = [_vp, _int, _int, _dbl, _dp, _i64, _dp, _i64, _dp, _i64,
+                                      ctypes.POINTER(_dbl), ctypes.POINTER(_dbl)]
+    lib.ces_step.argtypes = [_vp, _int, _int, _dbl, _dbl, _dp, _i64, _dp, _i64, _dp, _i64, _dp, _i64,
+                             ctypes.POINTER(_dbl), ctypes.POINTER(_dbl)]
+    lib.ces_step_host.argtypes = [_vp, _int, _int, _dbl, _dbl, _dp, _dp, _dp, _dp,
+                                  ctypes.POINTER(_dbl), ctypes.POINTER(_dbl)]
+    lib.ces_forward_map.argtypes = [_vp, _int, _dp, _i64, _dp, _dp, _dp, _i64, _dp, _i64]
+    lib.ces_buffer.argtypes = [_vp, ctypes.c_char_p, ctypes.POINTER(_vp), ctypes.POINTER(_i64),
+                               ctypes.POINTER(_i64), ctypes.POINTER(_i64)]
+    lib.ces_gemm.argtypes = [_vp, _int, _int, _i64, _i64, _i64, _dbl, _dp, _i64, _dp, _i64, _dbl, _dp, _i64]
+    lib.ces_potrf.argtypes = [_vp, _dp, _i64, _i64]
+    lib.ces_posv.argtypes = [_vp, _dp, _i64, _i64, _dp, _i64, _i64]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if fn.restype is ctypes.c_int and name not in ("ces_version", "ces_last_error", "ces_launch_count"):
+            fn.restype = _int
+    _lib = lib
+    return lib
+
+
+def check(status):
+    """Map a C status to the reference's exception conventions."""
+    if status == CES_OK:
+        return
+    msg = load().ces_last_error().decode("utf-8", "replace")
+    if status == CES_ERR_NOT_SPD:
+        raise np.linalg.LinAlgError(msg or "Matrix is not positive definite")
+    if status == CES_ERR_NOMEM:
+        raise MemoryError(msg)
+    if status in (CES_ERR_INVALID, CES_ERR_ALIGN):
+        raise ValueError(msg)
+    raise CesError(status, msg)
+
+
+def host_ptr(a):
+    """Address of a C-contiguous float64 numpy array (kept alive by the caller)."""
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data

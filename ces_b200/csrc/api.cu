@@ -1,0 +1,602 @@
+// C ABI of libces_b200.so (include/ces_b200.h): handle, problem set-up, the phases of one update.
+#include <cstring>
+#include <cstdlib>
+#include <string>
+#include <vector>
+#include "../../include/ces_b200.h"
+#include "kernels.h"
+
+using namespace ces;
+
+struct ces_handle_s {
+    int64_t p = 0, k = 0, Jl = 0, Jg = 0, cols = 0;
+    int rank = 0, nranks = 1;
+    int64_t ldJ = 0, ldp = 0, ldk = 0, ldD = 0, panel = 0;
+    cudaStream_t st = nullptr;
+    bool have_problem = false, gamma_diag = true, sigma_diag = true;
+    int last_rule = -1;
+    // problem data (device)
+    double *y = nullptr, *ginv_diag = nullptr, *Ginv = nullptr, *mu = nullptr, *ustar = nullptr;
+    double *sinv_diag = nullptr, *sig_diag = nullptr, *Sinv = nullptr, *Sigma0 = nullptr, *bprior = nullptr;
+    // per-step workspace (device)
+    double *sums = nullptr, *cvec = nullptr, *zvec = nullptr, *S = nullptr, *qpart = nullptr, *rowscratch = nullptr;
+    double *E_all = nullptr, *W = nullptr, *R = nullptr, *Ut_all = nullptr, *Z = nullptr, *Y = nullptr, *V = nullptr, *T = nullptr;
+    double *xi_pad = nullptr, *expU = nullptr;
+    double *Cuu = nullptr, *L = nullptr, *Linv = nullptr, *M = nullptr, *Minv = nullptr, *cb = nullptr;
+    double *D = nullptr, *ssq_partials = nullptr, *splitk_ws = nullptr;
+    int64_t ssq_cap = 0, splitk_cap = 0;
+    int syrk_splits = 1;
+    int* info = nullptr;
+    // host staging
+    double* hS = nullptr;   // pinned, S_COUNT doubles + 1 int
+    int* hinfo = nullptr;
+    double *stage_U = nullptr, *stage_G = nullptr, *stage_xi = nullptr, *stage_out = nullptr;
+    std::vector<void*> allocs;
+};
+
+namespace {
+
+const int64_t kLinvLd = CHOL_NB;
+
+int dalloc(ces_handle_t h, double** out, int64_t n) {
+    void* ptr = nullptr;
+    const size_t bytes = (size_t)(n < 1 ? 1 : n) * sizeof(double);
+    cudaError_t e = cudaMalloc(&ptr, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(CES_ERR_NOMEM, "cudaMalloc of %s%lld bytes failed", "", (long long)bytes);
+    }
+    e = cudaMemsetAsync(ptr, 0, bytes, h->st);
+    if (e != cudaSuccess) return fail(CES_ERR_CUDA, "cudaMemset failed%s", "");
+    h->allocs.push_back(ptr);
+    *out = static_cast<double*>(ptr);
+    return CES_OK;
+}
+
+double* e_block(ces_handle_t h, int r) { return h->E_all + (size_t)r * h->k * h->ldJ; }
+double* ut_block(ces_handle_t h, int r) { return h->Ut_all + (size_t)r * h->p * h->ldJ; }
+
+int check_info(ces_handle_t h, const char* what) {
+    CES_CUDA(cudaMemcpyAsync(h->hinfo, h->info, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CES_CUDA(cudaStreamSynchronize(h->st));
+    if (*h->hinfo != 0) {
+        const int piv = *h->hinfo;
+        CES_CUDA(cudaMemsetAsync(h->info, 0, sizeof(int), h->st));
+        return fail(CES_ERR_NOT_SPD, "%s: matrix is not positive definite (pivot %lld)", what, (long long)piv);
+    }
+    return CES_OK;
+}
+
+bool is_diagonal(const double* A, int64_t n) {
+    for (int64_t i = 0; i < n; ++i)
+        for (int64_t j = 0; j < n; ++j)
+            if (i != j && A[i * n + j] != 0.0) return false;
+    return true;
+}
+
+// Upload a dense n x n host matrix into a padded device buffer (ld = padded_ld(n)).
+int upload_square(ces_handle_t h, const double* host, int64_t n, double* dev, int64_t ld) {
+    CES_CUDA(cudaMemcpy2DAsync(dev, ld * sizeof(double), host, n * sizeof(double), n * sizeof(double), n,
+                               cudaMemcpyHostToDevice, h->st));
+    return CES_OK;
+}
+
+// dst (n x n, ld) <- inverse of the SPD matrix src (n x n host), via device Cholesky.
+int device_spd_inverse(ces_handle_t h, const double* host, int64_t n, double* dst, int64_t ld, const char* what) {
+    double *F = nullptr, *Fi = nullptr;
+    CES_CUDA(cudaMalloc(&F, (size_t)n * ld * sizeof(double)));
+    cudaError_t e = cudaMalloc(&Fi, (size_t)round_up(n, CHOL_NB) * kLinvLd * sizeof(double));
+    if (e != cudaSuccess) { cudaFree(F); cudaGetLastError(); return fail(CES_ERR_NOMEM, "cudaMalloc failed%s", ""); }
+    int s = CES_OK;
+    do {
+        if (cudaMemsetAsync(F, 0, (size_t)n * ld * sizeof(double), h->st) != cudaSuccess) { s = CES_ERR_CUDA; break; }
+        if ((s = upload_square(h, host, n, F, ld)) != CES_OK) break;
+        if ((s = potrf_lower(h->st, F, ld, n, Fi, kLinvLd, h->info)) != CES_OK) break;
+        if ((s = check_info(h, what)) != CES_OK) break;
+        if ((s = spd_inverse_from_factor(h->st, F, ld, n, Fi, kLinvLd, dst, ld)) != CES_OK) break;
+        if (cudaStreamSynchronize(h->st) != cudaSuccess) { s = fail(CES_ERR_CUDA, "device inverse failed%s", ""); break; }
+    } while (0);
+    cudaFree(F);
+    cudaFree(Fi);
+    return s;
+}
+
+int valid(ces_handle_t h, bool need_problem) {
+    if (!h) return fail(CES_ERR_INVALID, "null handle%s", "");
+    if (need_problem && !h->have_problem) return fail(CES_ERR_STATE, "ces_set_problem has not been called%s", "");
+    return CES_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ces_version(void) { return "ces_b200 0.1.0 sm_100a"; }
+const char* ces_last_error(void) { return g_last_error; }
+int64_t ces_launch_count(ces_handle_t) { return g_launches; }
+
+int ces_create(int64_t p, int64_t k, int64_t J_local, int64_t J_global, int rank, int nranks, int64_t cols_local,
+               void* stream, int64_t d_panel_bytes, ces_handle_t* out) {
+    if (!out) return fail(CES_ERR_INVALID, "ces_create: null output%s", "");
+    *out = nullptr;
+    if (p < 1 || k < 1 || J_local < 1 || J_global < 2 || nranks < 1 || rank < 0 || rank >= nranks || cols_local < 0 ||
+        cols_local > J_local || J_local * nranks < J_global)
+        return fail(CES_ERR_INVALID, "ces_create: inconsistent sizes%s", "");
+    if (p > (1 << 20) || k > (1 << 20) || J_global > (1ll << 30))
+        return fail(CES_ERR_INVALID, "ces_create: size out of range%s", "");
+    ces_handle_t h = new ces_handle_s();
+    h->p = p; h->k = k; h->Jl = J_local; h->Jg = J_global; h->cols = cols_local;
+    h->rank = rank; h->nranks = nranks;
+    h->st = static_cast<cudaStream_t>(stream);
+    h->ldJ = padded_ld(J_local);
+    h->ldp = padded_ld(p);
+    h->ldk = padded_ld(k);
+    if (d_panel_bytes <= 0) d_panel_bytes = 8ll << 30;
+    int64_t panel = d_panel_bytes / (8 * h->ldJ);
+    panel = panel / 128 * 128;
+    if (panel < 128) panel = 128;
+    if (panel > h->ldJ) panel = h->ldJ;
+    h->panel = panel;
+    h->ldD = panel;
+
+    int s = CES_OK;
+    const int ny = centre_rows_blocks(p > k ? p : k);
+    const int64_t tiles_per_rank = ceil_div(J_local, GEMM_BM) * ceil_div(J_local, GEMM_BN) + ceil_div(J_local, GEMM_BM) * ceil_div(J_local, panel);
+    h->ssq_cap = tiles_per_rank * nranks + 16;
+    // SYRK split-K: fill ~2 waves of 148 SMs with (lower tiles) x splits CTAs.
+    {
+        const int64_t tm = ceil_div(p, GEMM_BM);
+        const int64_t lower = tm * (tm + 1) / 2;
+        int64_t sp = ceil_div(296, lower);
+        const int64_t kb = ceil_div(h->ldJ, GEMM_BK);
+        if (sp > kb) sp = kb;
+        if (sp > 64) sp = 64;
+        if (sp < 1) sp = 1;
+        h->syrk_splits = (int)sp;
+        h->splitk_cap = sp * p * p;
+    }
+#define A_(ptr, n) if (s == CES_OK) s = dalloc(h, &h->ptr, (n))
+    A_(y, k); A_(ginv_diag, k); A_(mu, p); A_(ustar, p); A_(sinv_diag, p); A_(sig_diag, p); A_(bprior, p);
+    A_(sums, k + p); A_(cvec, k); A_(zvec, k); A_(S, S_COUNT); A_(cb, p);
+    A_(qpart, 2 * (int64_t)ny * h->ldJ); A_(rowscratch, (p > k ? p : k));
+    A_(E_all, (int64_t)nranks * k * h->ldJ); A_(W, k * h->ldJ);
+    A_(Ut_all, (int64_t)nranks * p * h->ldJ); A_(Z, p * h->ldJ); A_(V, p * h->ldJ); A_(T, p * h->ldJ);
+    A_(Cuu, p * h->ldp); A_(L, p * h->ldp); A_(Linv, round_up(p, CHOL_NB) * kLinvLd);
+    A_(D, h->ldJ * h->ldD);
+    A_(ssq_partials, h->ssq_cap); A_(splitk_ws, h->splitk_cap);
+#undef A_
+    if (s == CES_OK) {
+        void* ip = nullptr;
+        if (cudaMalloc(&ip, sizeof(int)) != cudaSuccess) s = fail(CES_ERR_NOMEM, "cudaMalloc failed%s", "");
+        else { h->info = static_cast<int*>(ip); h->allocs.push_back(ip); cudaMemsetAsync(ip, 0, sizeof(int), h->st); }
+    }
+    if (s == CES_OK) {
+        void* hp = nullptr;
+        if (cudaMallocHost(&hp, (S_COUNT + 2) * sizeof(double)) != cudaSuccess) s = fail(CES_ERR_NOMEM, "cudaMallocHost failed%s", "");
+        else { h->hS = static_cast<double*>(hp); h->hinfo = reinterpret_cast<int*>(h->hS + S_COUNT); *h->hinfo = 0; }
+    }
+    if (s == CES_OK && cudaStreamSynchronize(h->st) != cudaSuccess) s = fail(CES_ERR_CUDA, "workspace initialisation failed%s", "");
+    if (s != CES_OK) { ces_destroy(h); return s; }
+    *out = h;
+    return CES_OK;
+}
+
+int ces_destroy(ces_handle_t h) {
+    if (!h) return CES_OK;
+    cudaStreamSynchronize(h->st);
+    for (void* ptr : h->allocs) cudaFree(ptr);
+    if (h->hS) cudaFreeHost(h->hS);
+    delete h;
+    cudaGetLastError();
+    return CES_OK;
+}
+
+int ces_set_problem(ces_handle_t h, const double* y, const double* Gamma, const double* Sigma0, const double* mu,
+                    const double* ustar) {
+    CES_TRY(valid(h, false));
+    if (!y || !Gamma || !Sigma0 || !mu || !ustar) return fail(CES_ERR_INVALID, "ces_set_problem: null pointer%s", "");
+    const int64_t p = h->p, k = h->k;
+    h->have_problem = false;
+    CES_CUDA(cudaMemcpyAsync(h->y, y, k * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    CES_CUDA(cudaMemcpyAsync(h->mu, mu, p * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    CES_CUDA(cudaMemcpyAsync(h->ustar, ustar, p * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    CES_CUDA(cudaStreamSynchronize(h->st));
+
+    h->gamma_diag = is_diagonal(Gamma, k);
+    if (h->gamma_diag) {
+        std::vector<double> inv(k);
+        for (int64_t i = 0; i < k; ++i) {
+            if (!(Gamma[i * k + i] > 0.0)) return fail(CES_ERR_NOT_SPD, "Gamma: matrix is not positive definite (pivot %s%lld)", "", (long long)i + 1);
+            inv[i] = 1.0 / Gamma[i * k + i];
+        }
+        CES_CUDA(cudaMemcpyAsync(h->ginv_diag, inv.data(), k * sizeof(double), cudaMemcpyHostToDevice, h->st));
+        CES_CUDA(cudaStreamSynchronize(h->st));
+    } else {
+        if (!h->Ginv) { CES_TRY(dalloc(h, &h->Ginv, k * h->ldk)); }
+        if (!h->R) { CES_TRY(dalloc(h, &h->R, k * h->ldJ)); }
+        CES_TRY(device_spd_inverse(h, Gamma, k, h->Ginv, h->ldk, "Gamma"));
+    }
+
+    h->sigma_diag = is_diagonal(Sigma0, p);
+    if (h->sigma_diag) {
+        std::vector<double> inv(p), dg(p), bp(p);
+        for (int64_t i = 0; i < p; ++i) {
+            if (!(Sigma0[i * p + i] > 0.0)) return fail(CES_ERR_NOT_SPD, "sigma: matrix is not positive definite (pivot %s%lld)", "", (long long)i + 1);
+            dg[i] = Sigma0[i * p + i];
+            inv[i] = 1.0 / dg[i];
+            bp[i] = mu[i] / dg[i];
+        }
+        CES_CUDA(cudaMemcpyAsync(h->sinv_diag, inv.data(), p * sizeof(double), cudaMemcpyHostToDevice, h->st));
+        CES_CUDA(cudaMemcpyAsync(h->sig_diag, dg.data(), p * sizeof(double), cudaMemcpyHostToDevice, h->st));
+        CES_CUDA(cudaMemcpyAsync(h->bprior, bp.data(), p * sizeof(double), cudaMemcpyHostToDevice, h->st));
+        CES_CUDA(cudaStreamSynchronize(h->st));
+    } else {
+        if (!h->Sinv) { CES_TRY(dalloc(h, &h->Sinv, p * h->ldp)); }
+        if (!h->Sigma0) { CES_TRY(dalloc(h, &h->Sigma0, p * h->ldp)); }
+        if (!h->Y) { CES_TRY(dalloc(h, &h->Y, p * h->ldJ)); }
+        CES_TRY(upload_square(h, Sigma0, p, h->Sigma0, h->ldp));
+        CES_TRY(device_spd_inverse(h, Sigma0, p, h->Sinv, h->ldp, "sigma"));
+        CES_TRY(matvec(h->st, h->Sinv, h->ldp, p, h->mu, h->bprior));
+        CES_CUDA(cudaStreamSynchronize(h->st));
+    }
+    h->have_problem = true;
+    return CES_OK;
+}
+
+int ces_phase1_sums(ces_handle_t h, const double* U, int64_t ldu, const double* G, int64_t ldg) {
+    CES_TRY(valid(h, true));
+    if (!U || !G || ldu < h->cols || ldg < h->cols) return fail(CES_ERR_INVALID, "phase1: bad ensemble pointers%s", "");
+    if (h->cols == 0) {
+        CES_CUDA(cudaMemsetAsync(h->sums, 0, (h->k + h->p) * sizeof(double), h->st));
+        return CES_OK;
+    }
+    CES_TRY(row_sums(h->st, G, ldg, h->k, h->cols, h->sums));
+    CES_TRY(row_sums(h->st, U, ldu, h->p, h->cols, h->sums + h->k));
+    return CES_OK;
+}
+
+int ces_phase2_centre(ces_handle_t h, int rule, const double* U, int64_t ldu, const double* G, int64_t ldg) {
+    CES_TRY(valid(h, true));
+    if (rule < CES_RULE_EKS || rule > CES_RULE_EKI) return fail(CES_ERR_INVALID, "unknown update rule %s%lld", "", rule);
+    if (!U || !G) return fail(CES_ERR_INVALID, "phase2: null ensemble%s", "");
+    const int64_t p = h->p, k = h->k, ld = h->ldJ, cols = h->cols;
+    const double invJ = 1.0 / (double)h->Jg;
+    cudaStream_t st = h->st;
+    h->last_rule = rule;
+    double* E = e_block(h, h->rank);
+    double* Ut = ut_block(h, h->rank);
+    // --- forward outputs: E, R / W, c, z, data-space diagnostics
+    CES_TRY(centre_g(st, G, ldg, k, cols, h->sums, invJ, h->y, h->gamma_diag ? h->ginv_diag : nullptr, E,
+                     h->gamma_diag ? h->W : h->R, ld, h->cvec));
+    if (h->gamma_diag) {
+        CES_TRY(scale_vector(st, h->ginv_diag, h->cvec, h->zvec, k));
+    } else {
+        GemmCall g;   // W = Gamma^-1 R   (K2 of SURVEY.md section 2.2)
+        g.a_mode = A_MK; g.b_mode = B_KN;
+        g.M = (int)k; g.N = (int)h->Jl; g.K = (int)k;
+        g.A = h->Ginv; g.lda = h->ldk; g.B = h->R; g.ldb = ld; g.C = h->W; g.ldc = ld;
+        CES_TRY(gemm(st, g));
+        CES_TRY(matvec(st, h->Ginv, h->ldk, k, h->cvec, h->zvec));
+    }
+    const int nyk = centre_rows_blocks(k), nyp = centre_rows_blocks(p);
+    CES_TRY(data_forms(st, E, h->W, ld, k, h->cvec, h->zvec, h->qpart));
+    CES_TRY(finish_forms(st, h->qpart, nyk, ld, cols, true, h->S + S_SELF_DATA));
+    // --- parameters: U~, Z, parameter-space diagnostics
+    CES_TRY(centre_u(st, U, ldu, p, cols, h->sums + k, invJ, h->mu, h->ustar, h->sigma_diag ? h->sinv_diag : nullptr, Ut,
+                     h->sigma_diag ? h->Z : h->Y, ld, h->qpart));
+    CES_TRY(finish_forms(st, h->qpart, nyp, ld, cols, false, h->S + S_SELF_BIAS));
+    if (!h->sigma_diag) {
+        GemmCall g;   // Z = Sigma0^-1 (U - mu)
+        g.a_mode = A_MK; g.b_mode = B_KN;
+        g.M = (int)p; g.N = (int)h->Jl; g.K = (int)p;
+        g.A = h->Sinv; g.lda = h->ldp; g.B = h->Y; g.ldb = ld; g.C = h->Z; g.ldc = ld;
+        CES_TRY(gemm(st, g));
+    }
+    // --- local part of C^uu = U~ U~^T / (J-1) (+1e-8 I once)   (K6; :424 uses 1/J, :476/:512 use 1/(J-1))
+    {
+        GemmCall g;
+        g.a_mode = A_MK; g.b_mode = B_NK;
+        g.M = (int)p; g.N = (int)p; g.K = (int)h->Jl;
+        g.A = Ut; g.lda = ld; g.B = Ut; g.ldb = ld; g.C = h->Cuu; g.ldc = h->ldp;
+        g.alpha = (rule == CES_RULE_EKS) ? 1.0 / (double)h->Jg : 1.0 / (double)(h->Jg - 1);
+        g.flags = GEMM_C_LOWER_ONLY;
+        g.splits = h->syrk_splits; g.splitk_ws = h->splitk_ws;
+        g.diag_add = (h->rank == 0) ? 1e-8 : 0.0;
+        CES_TRY(gemm(st, g));
+    }
+    return CES_OK;
+}
+
+int ces_phase3_interact(ces_handle_t h, int rule) {
+    CES_TRY(valid(h, true));
+    if (rule != h->last_rule) return fail(CES_ERR_STATE, "phase3: rule differs from phase2%s", "");
+    const int64_t p = h->p, k = h->k, ld = h->ldJ;
+    cudaStream_t st = h->st;
+    // chol(C^uu)  (K7); EKI has no noise term and skips it
+    if (rule != CES_RULE_EKI) {
+        CES_CUDA(cudaMemcpy2DAsync(h->L, h->ldp * sizeof(double), h->Cuu, h->ldp * sizeof(double), p * sizeof(double), p,
+                                   cudaMemcpyDeviceToDevice, st));
+        CES_TRY(potrf_lower(st, h->L, h->ldp, p, h->Linv, kLinvLd, h->info));
+    }
+    // D = (1/J) E^T W by source block s (rows of D) and column panel (K3, K4); V = U~ D (K5)
+    int64_t npart = 0;
+    const double invJ = 1.0 / (double)h->Jg;
+    for (int64_t c0 = 0; c0 < h->Jl; c0 += h->panel) {
+        const int64_t nc = (h->Jl - c0) < h->panel ? (h->Jl - c0) : h->panel;
+        for (int s = 0; s < h->nranks; ++s) {
+            GemmCall g1;
+            g1.a_mode = A_KM; g1.b_mode = B_KN;
+            g1.M = (int)h->Jl; g1.N = (int)nc; g1.K = (int)k;
+            g1.A = e_block(h, s); g1.lda = ld;
+            g1.B = h->W + c0; g1.ldb = ld;
+            g1.C = h->D; g1.ldc = h->ldD;
+            g1.alpha = invJ;
+            const int tiles = gemm_tiles(g1.M, g1.N);
+            if (npart + tiles > h->ssq_cap) return fail(CES_ERR_STATE, "phase3: partial-sum buffer too small%s", "");
+            g1.ssq_partials = h->ssq_partials + npart;
+            npart += tiles;
+            CES_TRY(gemm(st, g1));
+            GemmCall g2;
+            g2.a_mode = A_MK; g2.b_mode = B_KN;
+            g2.M = (int)p; g2.N = (int)nc; g2.K = (int)h->Jl;
+            g2.A = ut_block(h, s); g2.lda = ld;
+            g2.B = h->D; g2.ldb = h->ldD;
+            g2.C = h->V + c0; g2.ldc = ld;
+            g2.beta = (s == 0) ? 0.0 : 1.0;
+            CES_TRY(gemm(st, g2));
+        }
+    }
+    CES_TRY(sum_vector(st, h->ssq_partials, npart, h->S + S_SSQ));
+    return CES_OK;
+}
+
+int ces_phase4a_drift(ces_handle_t h, double switch_) {
+    CES_TRY(valid(h, true));
+    if (h->last_rule != CES_RULE_ALDI_CONSTANT) return fail(CES_ERR_STATE, "phase4a is for aldi_constant only%s", "");
+    const int64_t p = h->p, ld = h->ldJ;
+    cudaStream_t st = h->st;
+    const double alphaJ = (double)(p + 1) / (double)h->Jg;
+    // drift = -(U~ D) - C Sigma0^-1 (U - mu) + switch * alpha_J * U~     (:515-517)
+    CES_TRY(axpbypcz(st, p, h->Jl, -1.0, h->V, ld, switch_ * alphaJ, nullptr, ut_block(h, h->rank), ld, 0.0, nullptr, nullptr,
+                     0, h->T, ld));
+    GemmCall g;
+    g.a_mode = A_MK; g.b_mode = B_KN;
+    g.M = (int)p; g.N = (int)h->Jl; g.K = (int)p;
+    g.A = h->Cuu; g.lda = h->ldp; g.B = h->Z; g.ldb = ld; g.C = h->T; g.ldc = ld;
+    g.alpha = -1.0; g.beta = 1.0;
+    CES_TRY(gemm(st, g));
+    CES_TRY(absmax(st, h->T, ld, p, h->cols, h->rowscratch, h->S + S_MAXDRIFT));
+    return CES_OK;
+}
+
+int ces_phase4_update(ces_handle_t h, int rule, int ts_kind, double fixed_h, const double* U, int64_t ldu,
+                      const double* xi, int64_t ldxi, double* Uout, int64_t ldo, double* hk_host, double* metrics_host) {
+    CES_TRY(valid(h, true));
+    if (rule != h->last_rule) return fail(CES_ERR_STATE, "phase4: rule differs from phase2%s", "");
+    if (!U || !Uout || (rule != CES_RULE_EKI && !xi)) return fail(CES_ERR_INVALID, "phase4: null pointer%s", "");
+    if (ts_kind != CES_TS_FROBENIUS && ts_kind != CES_TS_FIXED) return fail(CES_ERR_INVALID, "unknown step-size rule%s", "");
+    const int64_t p = h->p, ld = h->ldJ;
+    cudaStream_t st = h->st;
+    const double alphaJ = (double)(p + 1) / (double)h->Jg;
+    double* S = h->S;
+    double* Ut = ut_block(h, h->rank);
+
+    // noise operand: TMA needs a 16-byte aligned base and an even leading dimension
+    const double* xi_use = xi;
+    int64_t ldxi_use = ldxi;
+    if (xi && (((reinterpret_cast<uintptr_t>(xi) & 15) != 0) || (ldxi & 1))) {
+        if (!h->xi_pad) { CES_TRY(dalloc(h, &h->xi_pad, p * ld)); }
+        CES_TRY(pad_copy(st, xi, ldxi, p, h->cols, h->xi_pad, ld));
+        xi_use = h->xi_pad; ldxi_use = ld;
+    }
+
+    const int kind = (rule == CES_RULE_ALDI_CONSTANT) ? 2 : (ts_kind == CES_TS_FIXED ? 1 : 0);
+    CES_TRY(step_scalars(st, S, kind, fixed_h, alphaJ));
+
+    GemmCall noise;   // += sqrt(2h) chol(C) xi     (K8; L lower triangular -> skip the zero blocks)
+    noise.a_mode = A_MK; noise.b_mode = B_KN;
+    noise.M = (int)p; noise.N = (int)h->cols; noise.K = (int)p;
+    noise.A = h->L; noise.lda = h->ldp; noise.B = xi_use; noise.ldb = ldxi_use; noise.C = Uout; noise.ldc = ldo;
+    noise.alpha_dev = S + S_SQRT2H; noise.beta = 1.0; noise.flags = GEMM_A_LOWER_TRI;
+
+    if (h->cols > 0) {
+        if (rule == CES_RULE_ALDI) {
+            // U + h alpha_J U~ - h V - h C Z + sqrt(2h) L xi      (:484-488)
+            CES_TRY(axpbypcz(st, p, h->cols, 1.0, U, ldu, 1.0, S + S_H_ALPHA, Ut, ld, 1.0, S + S_NEG_H, h->V, ld, Uout, ldo));
+            GemmCall g;
+            g.a_mode = A_MK; g.b_mode = B_KN;
+            g.M = (int)p; g.N = (int)h->cols; g.K = (int)p;
+            g.A = h->Cuu; g.lda = h->ldp; g.B = h->Z; g.ldb = ld; g.C = Uout; g.ldc = ldo;
+            g.alpha_dev = S + S_NEG_H; g.beta = 1.0;
+            CES_TRY(gemm(st, g));
+            CES_TRY(gemm(st, noise));
+        } else if (rule == CES_RULE_ALDI_CONSTANT) {
+            // U + h drift + sqrt(2h) L xi                         (:525-527)
+            CES_TRY(axpbypcz(st, p, h->cols, 1.0, U, ldu, 1.0, S + S_H, h->T, ld, 0.0, nullptr, nullptr, 0, Uout, ldo));
+            CES_TRY(gemm(st, noise));
+        } else if (rule == CES_RULE_EKI) {
+            CES_TRY(axpbypcz(st, p, h->cols, 1.0, U, ldu, 1.0, S + S_NEG_H, h->V, ld, 0.0, nullptr, nullptr, 0, Uout, ldo));
+        } else {
+            // semi-implicit EKS (:443-447) with (I + h C S^-1)^-1 = S (S + h C)^-1   
+            if (!h->M) { CES_TRY(dalloc(h, &h->M, p * h->ldp)); }
+            if (!h->Minv) { CES_TRY(dalloc(h, &h->Minv, round_up(p, CHOL_NB) * kLinvLd)); }
+            CES_TRY(form_implicit(st, h->Cuu, h->ldp, h->sigma_diag ? nullptr : h->Sigma0, h->ldp, h->sig_diag, S + S_H, p,
+                                  h->M, h->ldp));
+            CES_TRY(potrf_lower(st, h->M, h->ldp, p, h->Minv, kLinvLd, h->info));
+            // T = U - h V + h C Sigma0^-1 mu
+            CES_TRY(axpbypcz(st, p, h->cols, 1.0, U, ldu, 1.0, S + S_NEG_H, h->V, ld, 0.0, nullptr, nullptr, 0, h->T, ld));
+            CES_TRY(matvec(st, h->Cuu, h->ldp, p, h->bprior, h->cb));
+            CES_TRY(add_col_vector(st, h->T, ld, p, h->cols, h->cb, 1.0, S + S_H));
+            CES_TRY(trsm_lower(st, h->M, h->ldp, p, h->Minv, kLinvLd, h->T, ld, h->cols, false));
+            CES_TRY(trsm_lower(st, h->M, h->ldp, p, h->Minv, kLinvLd, h->T, ld, h->cols, true));
+            if (h->sigma_diag) {
+                CES_TRY(row_scale(st, h->sig_diag, h->T, ld, p, h->cols));
+                CES_TRY(axpbypcz(st, p, h->cols, 1.0, h->T, ld, 0.0, nullptr, nullptr, 0, 0.0, nullptr, nullptr, 0, Uout, ldo));
+            } else {
+                GemmCall g;
+                g.a_mode = A_MK; g.b_mode = B_KN;
+                g.M = (int)p; g.N = (int)h->cols; g.K = (int)p;
+                g.A = h->Sigma0; g.lda = h->ldp; g.B = h->T; g.ldb = ld; g.C = Uout; g.ldc = ldo;
+                CES_TRY(gemm(st, g));
+            }
+            CES_TRY(gemm(st, noise));
+        }
+    }
+    CES_CUDA(cudaMemcpyAsync(h->hS, S, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CES_TRY(check_info(h, "cov(U)"));   // synchronises the stream
+    if (hk_host) *hk_host = h->hS[S_H];
+    if (metrics_host) {
+        const double J = (double)h->Jg;
+        metrics_host[0] = h->hS[S_SELF_BIAS] / J;
+        metrics_host[1] = h->hS[S_BIAS] / J;
+        metrics_host[2] = h->hS[S_SELF_DATA] / J;
+        metrics_host[3] = h->hS[S_BIAS_DATA] / J;
+    }
+    return CES_OK;
+}
+
+int ces_step(ces_handle_t h, int rule, int ts_kind, double fixed_h, double switch_, const double* U, int64_t ldu,
+             const double* G, int64_t ldg, const double* xi, int64_t ldxi, double* Uout, int64_t ldo, double* hk_host,
+             double* metrics_host) {
+    CES_TRY(valid(h, true));
+    if (h->nranks != 1) return fail(CES_ERR_STATE, "ces_step is single-GPU; use the phases with nranks > 1%s", "");
+    CES_TRY(ces_phase1_sums(h, U, ldu, G, ldg));
+    CES_TRY(ces_phase2_centre(h, rule, U, ldu, G, ldg));
+    CES_TRY(ces_phase3_interact(h, rule));
+    if (rule == CES_RULE_ALDI_CONSTANT) CES_TRY(ces_phase4a_drift(h, switch_));
+    return ces_phase4_update(h, rule, ts_kind, fixed_h, U, ldu, xi, ldxi, Uout, ldo, hk_host, metrics_host);
+}
+
+int ces_step_host(ces_handle_t h, int rule, int ts_kind, double fixed_h, double switch_, const double* U, const double* G,
+                  const double* xi, double* Uout, double* hk_host, double* metrics_host) {
+    CES_TRY(valid(h, true));
+    if (h->nranks != 1) return fail(CES_ERR_STATE, "ces_step_host is single-GPU%s", "");
+    if (!U || !G || !Uout) return fail(CES_ERR_INVALID, "ces_step_host: null pointer%s", "");
+    const int64_t p = h->p, k = h->k, J = h->Jl, ld = h->ldJ;
+    if (!h->stage_U) {
+        CES_TRY(dalloc(h, &h->stage_U, p * ld));
+        CES_TRY(dalloc(h, &h->stage_G, k * ld));
+        CES_TRY(dalloc(h, &h->stage_xi, p * ld));
+        CES_TRY(dalloc(h, &h->stage_out, p * ld));
+    }
+    const size_t wb = J * sizeof(double), pb = ld * sizeof(double);
+    CES_CUDA(cudaMemcpy2DAsync(h->stage_U, pb, U, wb, wb, p, cudaMemcpyHostToDevice, h->st));
+    CES_CUDA(cudaMemcpy2DAsync(h->stage_G, pb, G, wb, wb, k, cudaMemcpyHostToDevice, h->st));
+    if (xi) CES_CUDA(cudaMemcpy2DAsync(h->stage_xi, pb, xi, wb, wb, p, cudaMemcpyHostToDevice, h->st));
+    CES_TRY(ces_step(h, rule, ts_kind, fixed_h, switch_, h->stage_U, ld, h->stage_G, ld, xi ? h->stage_xi : nullptr, ld,
+                     h->stage_out, ld, hk_host, metrics_host));
+    CES_CUDA(cudaMemcpy2DAsync(Uout, wb, h->stage_out, pb, wb, p, cudaMemcpyDeviceToHost, h->st));
+    CES_CUDA(cudaStreamSynchronize(h->st));
+    return CES_OK;
+}
+
+int ces_forward_map(ces_handle_t h, int map_kind, const double* A, int64_t lda, const double* b, const double* params,
+                    const double* U, int64_t ldu, double* G, int64_t ldg) {
+    CES_TRY(valid(h, false));
+    if (!U || !G) return fail(CES_ERR_INVALID, "ces_forward_map: null ensemble%s", "");
+    const int64_t p = h->p, k = h->k, cols = h->cols, ld = h->ldJ;
+    if (cols == 0) return CES_OK;
+    cudaStream_t st = h->st;
+    if (map_kind == CES_MAP_LINEAL || map_kind == CES_MAP_LINEAL_LOG) {
+        if (!A) return fail(CES_ERR_INVALID, "ces_forward_map: lineal needs A%s", "");
+        const double* B = U;
+        int64_t ldb = ldu;
+        const bool misaligned = ((reinterpret_cast<uintptr_t>(U) & 15) != 0) || (ldu & 1);
+        if (map_kind == CES_MAP_LINEAL_LOG || misaligned) {
+            if (!h->expU) { CES_TRY(dalloc(h, &h->expU, p * ld)); }
+            if (map_kind == CES_MAP_LINEAL_LOG) CES_TRY(exp_map(st, U, ldu, p, cols, h->expU, ld));
+            else CES_TRY(pad_copy(st, U, ldu, p, cols, h->expU, ld));
+            B = h->expU; ldb = ld;
+        }
+        GemmCall g;
+        g.a_mode = A_MK; g.b_mode = B_KN;
+        g.M = (int)k; g.N = (int)cols; g.K = (int)p;
+        g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = G; g.ldc = ldg;
+        CES_TRY(gemm(st, g));
+        if (b) CES_TRY(add_col_vector(st, G, ldg, k, cols, b, 1.0, nullptr));
+        return CES_OK;
+    }
+    if (map_kind == CES_MAP_ELLIPTIC || map_kind == CES_MAP_BANANA) {
+        if (p != 2 || k != 2 || !params) return fail(CES_ERR_INVALID, "ces_forward_map: elliptic/banana need p = k = 2 and params%s", "");
+        if (map_kind == CES_MAP_ELLIPTIC) return elliptic_map(st, U, ldu, cols, params[0], params[1], G, ldg);
+        return banana_map(st, U, ldu, cols, params[0], params[1], G, ldg);
+    }
+    return fail(CES_ERR_INVALID, "ces_forward_map: unknown map kind %s%lld", "", map_kind);
+}
+
+int ces_buffer(ces_handle_t h, const char* name, double** ptr, int64_t* rows, int64_t* cols, int64_t* ld) {
+    CES_TRY(valid(h, false));
+    if (!name || !ptr) return fail(CES_ERR_INVALID, "ces_buffer: null argument%s", "");
+    const std::string n(name);
+    double* q = nullptr;
+    int64_t r = 0, c = 0, l = 0;
+    if (n == "sums") { q = h->sums; r = 1; c = h->k + h->p; l = c; }
+    else if (n == "cuu") { q = h->Cuu; r = h->p; c = h->ldp; l = h->ldp; }
+    else if (n == "chol") { q = h->L; r = h->p; c = h->ldp; l = h->ldp; }
+    else if (n == "e_all") { q = h->E_all; r = h->nranks * h->k; c = h->ldJ; l = h->ldJ; }
+    else if (n == "ut_all") { q = h->Ut_all; r = h->nranks * h->p; c = h->ldJ; l = h->ldJ; }
+    else if (n == "scalars") { q = h->S; r = 1; c = S_COUNT; l = S_COUNT; }
+    else if (n == "w") { q = h->W; r = h->k; c = h->ldJ; l = h->ldJ; }
+    else if (n == "v") { q = h->V; r = h->p; c = h->ldJ; l = h->ldJ; }
+    else if (n == "z") { q = h->Z; r = h->p; c = h->ldJ; l = h->ldJ; }
+    else if (n == "d_panel") { q = h->D; r = h->ldJ; c = h->ldD; l = h->ldD; }
+    else return fail(CES_ERR_INVALID, "ces_buffer: unknown buffer '%s'", name);
+    *ptr = q;
+    if (rows) *rows = r;
+    if (cols) *cols = c;
+    if (ld) *ld = l;
+    return CES_OK;
+}
+
+int ces_gemm(void* stream, int a_mode, int b_mode, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
+             const double* B, int64_t ldb, double beta, double* C, int64_t ldc) {
+    if (a_mode < 0 || a_mode > 1 || b_mode < 0 || b_mode > 1 || M > (1ll << 30) || N > (1ll << 30) || K > (1ll << 30))
+        return fail(CES_ERR_INVALID, "ces_gemm: bad mode or size%s", "");
+    GemmCall g;
+    g.a_mode = a_mode; g.b_mode = b_mode;
+    g.M = (int)M; g.N = (int)N; g.K = (int)K;
+    g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
+    g.alpha = alpha; g.beta = beta;
+    return gemm(static_cast<cudaStream_t>(stream), g);
+}
+
+int ces_potrf(void* stream, double* A, int64_t ld, int64_t n) {
+    if (!A || n < 1 || ld < n) return fail(CES_ERR_INVALID, "ces_potrf: bad argument%s", "");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double* Linv = nullptr;
+    int* info = nullptr;
+    CES_CUDA(cudaMalloc(&Linv, (size_t)round_up(n, CHOL_NB) * kLinvLd * sizeof(double)));
+    if (cudaMalloc(&info, sizeof(int)) != cudaSuccess) { cudaFree(Linv); return fail(CES_ERR_NOMEM, "cudaMalloc failed%s", ""); }
+    cudaMemsetAsync(info, 0, sizeof(int), st);
+    int s = potrf_lower(st, A, ld, n, Linv, kLinvLd, info);
+    int hinfo = 0;
+    if (s == CES_OK && cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) s = CES_ERR_CUDA;
+    if (cudaStreamSynchronize(st) != cudaSuccess && s == CES_OK) s = fail(CES_ERR_CUDA, "ces_potrf: kernel failure%s", "");
+    cudaFree(Linv);
+    cudaFree(info);
+    if (s == CES_OK && hinfo != 0) return fail(CES_ERR_NOT_SPD, "ces_potrf: matrix is not positive definite (pivot %s%lld)", "", hinfo);
+    return s;
+}
+
+int ces_posv(void* stream, double* A, int64_t lda, int64_t n, double* B, int64_t ldb, int64_t nrhs) {
+    if (!A || !B || n < 1 || nrhs < 1 || lda < n || ldb < nrhs) return fail(CES_ERR_INVALID, "ces_posv: bad argument%s", "");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double* Linv = nullptr;
+    int* info = nullptr;
+    CES_CUDA(cudaMalloc(&Linv, (size_t)round_up(n, CHOL_NB) * kLinvLd * sizeof(double)));
+    if (cudaMalloc(&info, sizeof(int)) != cudaSuccess) { cudaFree(Linv); return fail(CES_ERR_NOMEM, "cudaMalloc failed%s", ""); }
+    cudaMemsetAsync(info, 0, sizeof(int), st);
+    int s = potrf_lower(st, A, lda, n, Linv, kLinvLd, info);
+    int hinfo = 0;
+    if (s == CES_OK && cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) s = CES_ERR_CUDA;
+    if (s == CES_OK && cudaStreamSynchronize(st) != cudaSuccess) s = fail(CES_ERR_CUDA, "ces_posv: kernel failure%s", "");
+    if (s == CES_OK && hinfo != 0) s = fail(CES_ERR_NOT_SPD, "ces_posv: matrix is not positive definite (pivot %s%lld)", "", hinfo);
+    if (s == CES_OK) s = trsm_lower(st, A, lda, n, Linv, kLinvLd, B, ldb, nrhs, false);
+    if (s == CES_OK) s = trsm_lower(st, A, lda, n, Linv, kLinvLd, B, ldb, nrhs, true);
+    if (cudaStreamSynchronize(st) != cudaSuccess && s == CES_OK) s = fail(CES_ERR_CUDA, "ces_posv: kernel failure%s", "");
+    cudaFree(Linv);
+    cudaFree(info);
+    return s;
+}
+
+}  // extern "C"

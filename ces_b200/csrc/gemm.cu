@@ -1,0 +1,73 @@
+// Host launcher of the FP64 DMMA GEMM family (see gemm.cuh).
+#include "gemm.cuh"
+#include "kernels.h"
+
+namespace ces {
+
+thread_local char g_last_error[512] = "";
+long long g_launches = 0;
+
+template <int AM, int BM_>
+static int launch_one(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& a, dim3 grid) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CES_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<AM, BM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+        attr_set = true;
+    }
+    gemm_dmma_kernel<AM, BM_><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ma, mb, a);
+    CES_LAUNCHED(1);
+    return CES_OK;
+}
+
+int gemm_tiles(int M, int N) { return (int)(ceil_div(M, GEMM_BM) * ceil_div(N, GEMM_BN)); }
+
+int gemm(cudaStream_t st, const GemmCall& c) {
+    if (c.M < 1 || c.N < 1 || c.K < 1 || !c.A || !c.B || !c.C) return fail(CES_ERR_INVALID, "gemm: bad shape or null operand%s", "");
+    CUtensorMap ma, mb;
+    if (c.a_mode == A_MK) CES_TRY(make_map_2d(&ma, c.A, c.K, c.M, c.lda, 16, 128));
+    else                  CES_TRY(make_map_2d(&ma, c.A, c.M, c.K, c.lda, 16, 16));
+    if (c.b_mode == B_NK) CES_TRY(make_map_2d(&mb, c.B, c.K, c.N, c.ldb, 16, 128));
+    else                  CES_TRY(make_map_2d(&mb, c.B, c.N, c.K, c.ldb, 16, 16));
+
+    GemmArgs a;
+    a.M = c.M; a.N = c.N; a.K = c.K;
+    a.C = c.C; a.ldc = c.ldc;
+    a.alpha = c.alpha; a.beta = c.beta; a.alpha_dev = c.alpha_dev;
+    a.ssq_partials = c.ssq_partials;
+    a.tiles_m = (int)ceil_div(c.M, GEMM_BM);
+    a.tiles_n = (int)ceil_div(c.N, GEMM_BN);
+    a.group_m = c.group_m > 0 ? c.group_m : 8;
+    a.flags = c.flags;
+    a.splits = 1;
+    a.kblocks_per_split = 0;
+    a.splitk_ws = nullptr;
+    const int kb_total = (int)ceil_div(c.K, GEMM_BK);
+    int splits = c.splits > 1 ? c.splits : 1;
+    if (splits > kb_total) splits = kb_total;
+    // With a workspace the kernel writes raw partial products and the reduce kernel applies
+    // alpha / beta / diag_add and mirrors symmetric results (also used with a single split).
+    const bool via_ws = c.splitk_ws != nullptr;
+    if (splits > 1 && !via_ws) return fail(CES_ERR_INVALID, "gemm: split-K needs a workspace%s", "");
+    if (via_ws && c.ssq_partials) return fail(CES_ERR_INVALID, "gemm: workspace path cannot produce sum-of-squares partials%s", "");
+    a.kblocks_per_split = (int)ceil_div(kb_total, splits);
+    a.splits = (int)ceil_div(kb_total, a.kblocks_per_split);
+    a.splitk_ws = c.splitk_ws;
+    dim3 grid((unsigned)(a.tiles_m * a.tiles_n), 1, (unsigned)a.splits);
+    int s;
+    if (c.a_mode == A_MK && c.b_mode == B_KN) s = launch_one<0, 0>(st, ma, mb, a, grid);
+    else if (c.a_mode == A_KM && c.b_mode == B_KN) s = launch_one<1, 0>(st, ma, mb, a, grid);
+    else if (c.a_mode == A_MK && c.b_mode == B_NK) s = launch_one<0, 1>(st, ma, mb, a, grid);
+    else s = launch_one<1, 1>(st, ma, mb, a, grid);
+    CES_TRY(s);
+    if (via_ws) {
+        const long long total = (long long)c.M * c.N;
+        const int threads = 256;
+        splitk_reduce_kernel<<<(unsigned)ceil_div(total, threads), threads, 0, st>>>(
+            c.splitk_ws, a.splits, c.M, c.N, c.C, c.ldc, c.alpha, c.alpha_dev, c.beta, c.diag_add,
+            (c.flags & GEMM_C_LOWER_ONLY) ? 1 : 0);
+        CES_LAUNCHED(1);
+    }
+    return CES_OK;
+}
+
+}  // namespace ces

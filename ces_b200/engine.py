@@ -1,0 +1,196 @@
+"""Per-GPU engine: owns one ``ces_handle_t`` and drives the phases of an update.
+
+Torch is plumbing only: device buffers (``torch.Tensor`` as allocations), the
+current CUDA stream and ``torch.distributed`` for the collectives between phases
+when the ensemble is sharded by particle columns over several GPUs
+(SURVEY.md section 8e).  All arithmetic happens in libces_b200.so.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+_METRIC_KEYS = ("self-bias", "bias", "self-bias-data", "bias-data")
+
+
+def shard_width(J, nranks):
+    """Common (padded) shard width: every rank holds ceil(J / nranks) columns, the
+    trailing ranks possibly fewer true ones."""
+    return -(-J // nranks)
+
+
+def shard_range(J, rank, nranks):
+    w = shard_width(J, nranks)
+    lo = min(J, rank * w)
+    return lo, min(J, lo + w)
+
+
+class _DeviceView(object):
+    """Zero-copy torch view of a library-owned device buffer (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {
+            "shape": tuple(int(s) for s in shape), "typestr": "<f8", "data": (int(ptr), False),
+            "version": 2, "strides": None,
+        }
+
+
+class Engine(object):
+    """One sampler's device state on the current CUDA device.
+
+    p, k      parameter / observation dimensions (``enka.__init__``, ces/calibrate.py:14-22)
+    J         global ensemble size
+    group     torch.distributed process group when the ensemble is column-sharded
+              (None: single GPU).  Rank r owns columns ``shard_range(J, r, nranks)``.
+    """
+
+    def __init__(self, p, k, J, group=None, d_panel_bytes=0):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("ces_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.torch = torch
+        self.lib = _lib.load()
+        self.p, self.k, self.J = int(p), int(k), int(J)
+        self.group = group
+        if group is not None:
+            import torch.distributed as dist
+
+            self.dist = dist
+            self.rank, self.nranks = dist.get_rank(group), dist.get_world_size(group)
+        else:
+            self.dist = None
+            self.rank, self.nranks = 0, 1
+        self.Jl = shard_width(self.J, self.nranks)
+        lo, hi = shard_range(self.J, self.rank, self.nranks)
+        self.col_lo, self.col_hi = lo, hi
+        self.cols = hi - lo
+        self.stream = torch.cuda.current_stream()
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.ces_create(self.p, self.k, self.Jl, self.J, self.rank, self.nranks, self.cols,
+                                       ctypes.c_void_p(self.stream.cuda_stream), int(d_panel_bytes), ctypes.byref(h)))
+        self.h = h
+        self._views = {}
+        self._hk = ctypes.c_double()
+        self._met = (ctypes.c_double * 4)()
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ces_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ problem data
+    def set_problem(self, y_obs, Gamma, sigma, mu, ustar):
+        y = np.ascontiguousarray(np.asarray(y_obs, dtype=np.float64).reshape(self.k))
+        Gam = np.ascontiguousarray(np.asarray(Gamma, dtype=np.float64).reshape(self.k, self.k))
+        Sig = np.ascontiguousarray(np.asarray(sigma, dtype=np.float64).reshape(self.p, self.p))
+        m = np.ascontiguousarray(np.asarray(mu, dtype=np.float64).reshape(self.p))
+        us = np.ascontiguousarray(np.asarray(ustar, dtype=np.float64).reshape(self.p))
+        _lib.check(self.lib.ces_set_problem(self.h, _lib.host_ptr(y), _lib.host_ptr(Gam), _lib.host_ptr(Sig),
+                                            _lib.host_ptr(m), _lib.host_ptr(us)))
+
+    # ------------------------------------------------------------------ buffers
+    def buffer(self, name):
+        """Torch view (rows x ld) of a named library buffer (see ces_buffer in the header)."""
+        if name not in self._views:
+            ptr, rows, cols, ld = ctypes.c_void_p(), ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+            _lib.check(self.lib.ces_buffer(self.h, name.encode(), ctypes.byref(ptr), ctypes.byref(rows),
+                                           ctypes.byref(cols), ctypes.byref(ld)))
+            view = _DeviceView(ptr.value, (rows.value, ld.value))
+            self._views[name] = self.torch.as_tensor(view, device="cuda")
+        return self._views[name]
+
+    def launch_count(self):
+        return int(self.lib.ces_launch_count(self.h))
+
+    @staticmethod
+    def _dev(t):
+        assert t.is_cuda and t.dtype.is_floating_point and t.element_size() == 8 and t.stride(1) == 1, \
+            "device ensembles must be float64 CUDA tensors with the particle axis contiguous"
+        return ctypes.c_void_p(t.data_ptr()), int(t.stride(0))
+
+    # ------------------------------------------------------------------ one update
+    def step(self, rule, U, G, xi, out=None, fixed_h=None, switch=1.0):
+        """One update on this rank's columns.  U (p, cols), G (k, cols), xi (p, cols) are float64 CUDA
+        tensors; returns (U_next, hk, metrics dict).  ``fixed_h`` selects the 'constant' step size."""
+        torch = self.torch
+        r = _lib.RULES[rule]
+        ts = _lib.TS_FIXED if fixed_h is not None else _lib.TS_FROBENIUS
+        fh = float(fixed_h) if fixed_h is not None else 0.0
+        if out is None:
+            out = torch.empty_like(U)
+        Up, ldu = self._dev(U)
+        Gp, ldg = self._dev(G)
+        Op, ldo = self._dev(out)
+        if xi is not None:
+            Xp, ldx = self._dev(xi)
+        else:
+            Xp, ldx = ctypes.c_void_p(0), 0
+        lib, h = self.lib, self.h
+        if self.nranks == 1:
+            _lib.check(lib.ces_step(h, r, ts, fh, float(switch), Up, ldu, Gp, ldg, Xp, ldx, Op, ldo,
+                                    ctypes.byref(self._hk), self._met))
+        else:
+            dist, grp = self.dist, self.group
+            _lib.check(lib.ces_phase1_sums(h, Up, ldu, Gp, ldg))
+            dist.all_reduce(self.buffer("sums"), group=grp)
+            _lib.check(lib.ces_phase2_centre(h, r, Up, ldu, Gp, ldg))
+            dist.all_reduce(self.buffer("cuu"), group=grp)
+            e_all, ut_all = self.buffer("e_all"), self.buffer("ut_all")
+            dist.all_gather_into_tensor(e_all, e_all[self.rank * self.k:(self.rank + 1) * self.k], group=grp)
+            dist.all_gather_into_tensor(ut_all, ut_all[self.rank * self.p:(self.rank + 1) * self.p], group=grp)
+            _lib.check(lib.ces_phase3_interact(h, r))
+            scal = self.buffer("scalars")
+            dist.all_reduce(scal[0, 0:5], group=grp)
+            if rule == "aldi_constant":
+                _lib.check(lib.ces_phase4a_drift(h, float(switch)))
+                dist.all_reduce(scal[0, 5:6], op=dist.ReduceOp.MAX, group=grp)
+            _lib.check(lib.ces_phase4_update(h, r, ts, fh, Up, ldu, Xp, ldx, Op, ldo,
+                                             ctypes.byref(self._hk), self._met))
+        met = {key: float(self._met[i]) for i, key in enumerate(_METRIC_KEYS)}
+        return out, float(self._hk.value), met
+
+    def step_host(self, rule, U, G, xi, fixed_h=None, switch=1.0):
+        """The same update on host numpy arrays (single GPU): the copies to and from the device are part
+        of the call.  This is what ``sampling.eks_update*`` invoke."""
+        if self.nranks != 1:
+            raise RuntimeError("step_host is single-GPU; shard device tensors and call step()")
+        r = _lib.RULES[rule]
+        ts = _lib.TS_FIXED if fixed_h is not None else _lib.TS_FROBENIUS
+        fh = float(fixed_h) if fixed_h is not None else 0.0
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        G = np.ascontiguousarray(G, dtype=np.float64)
+        assert U.shape == (self.p, self.J) and G.shape == (self.k, self.J), (U.shape, G.shape)
+        out = np.empty_like(U)
+        if xi is not None:
+            xi = np.ascontiguousarray(xi, dtype=np.float64)
+            assert xi.shape == U.shape
+            xp = _lib.host_ptr(xi)
+        else:
+            xp = None
+        _lib.check(self.lib.ces_step_host(self.h, r, ts, fh, float(switch), _lib.host_ptr(U), _lib.host_ptr(G), xp,
+                                          _lib.host_ptr(out), ctypes.byref(self._hk), self._met))
+        met = {key: float(self._met[i]) for i, key in enumerate(_METRIC_KEYS)}
+        return out, float(self._hk.value), met
+
+    # ------------------------------------------------------------------ forward maps
+    def forward_map(self, kind, U, G, A=None, lda=0, b=None, params=None):
+        """G[:, j] = model(U[:, j]) on the device for the ces.utils maps (enka.G_ens)."""
+        Up, ldu = self._dev(U)
+        Gp, ldg = self._dev(G)
+        Ap = ctypes.c_void_p(A.data_ptr()) if A is not None else None
+        bp = ctypes.c_void_p(b.data_ptr()) if b is not None else None
+        if params is not None:
+            pr = np.ascontiguousarray(params, dtype=np.float64)
+            pp = _lib.host_ptr(pr)
+        else:
+            pp = None
+        _lib.check(self.lib.ces_forward_map(self.h, _lib.MAPS[kind], Ap, int(lda), bp, pp, Up, ldu, Gp, ldg))
+        return G

@@ -1,0 +1,141 @@
+/* ces_b200 -- C ABI of the B200-native ensemble Kalman update (libces_b200.so).
+ *
+ * Drop-in boundary for the numpy update of agarbuno/ces `ces/calibrate.py`.  The reference has no
+ * FFI of its own (it is pure Python); these entry points are what `ces_b200/calibrate.py` binds
+ * through ctypes in place of the numpy/LAPACK calls of
+ *     sampling.eks_update                (ces/calibrate.py:418-449)
+ *     sampling.eks_update_aldi           (ces/calibrate.py:451-490)   default rule
+ *     sampling.eks_update_aldi_constant  (ces/calibrate.py:492-529)
+ *     sampling.timestep_method           (ces/calibrate.py:243-267)
+ *     enka.G_ens over the ces.utils maps (ces/calibrate.py:106-130, ces/utils.py:5-122)
+ * INTEGRATION.md shows the reference-side stub a maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; every matrix is row-major float64 with an explicit leading dimension (in
+ *     elements); ensembles are (p x J) and (k x J) with the particle index contiguous, exactly the
+ *     reference's layout (ces/calibrate.py:56-57, 123).
+ *   - `*_dev` pointers are CUDA device pointers, `*_host` pointers are host pointers.
+ *   - every function returns an int status: 0 ok, <0 error (CES_ERR_*), message via ces_last_error().
+ *     CES_ERR_NOT_SPD maps to numpy.linalg.LinAlgError on the Python side.  No C++ exception crosses.
+ *   - a handle is not re-entrant; different handles may be used from different threads.  All work of a
+ *     handle is issued on the stream given at creation.
+ *   - multi-GPU: one handle per process/GPU, the ensemble is sharded by particle columns.  The library
+ *     performs no communication itself; the host runs the collectives named below between the phases
+ *     (torch.distributed / NCCL in ces_b200/calibrate.py).
+ */
+#ifndef CES_B200_H
+#define CES_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CES_OK 0
+#define CES_ERR_INVALID (-1)
+#define CES_ERR_STATE (-2)
+#define CES_ERR_ALIGN (-3)
+#define CES_ERR_NOT_SPD (-4)
+#define CES_ERR_CUDA (-5)
+#define CES_ERR_NOMEM (-6)
+
+/* update rules (ces/calibrate.py:364-369) */
+#define CES_RULE_EKS 0            /* :418-449 semi-implicit, biased covariance                       */
+#define CES_RULE_ALDI 1           /* :451-490 default                                                */
+#define CES_RULE_ALDI_CONSTANT 2  /* :492-529 h = 0.1 / max|drift|                                   */
+#define CES_RULE_EKI 3            /* U - h (U - ubar) D, the part shared by all three    */
+
+/* step-size rules (ces/calibrate.py:247-260) */
+#define CES_TS_FROBENIUS 0        /* h = 1 / (||D||_F + 1e-8), :248                                  */
+#define CES_TS_FIXED 1            /* h given by the caller ('constant', and 'mix' after spin-up)     */
+
+/* forward maps (ces/utils.py) */
+#define CES_MAP_LINEAL 0          /* A theta + b           :25-31  */
+#define CES_MAP_LINEAL_LOG 1      /* A exp(phi) + b        :39-42  */
+#define CES_MAP_ELLIPTIC 2        /* :72-89  (p = 2, k = 2; params = {x1, x2})                       */
+#define CES_MAP_BANANA 3          /* :116-122 (p = 2, k = 2; params = {a, b})                        */
+
+typedef struct ces_handle_s* ces_handle_t;
+
+/* Library / build identification ("ces_b200 <version> sm_100a"). */
+const char* ces_version(void);
+/* Message of the last failing call on this thread. */
+const char* ces_last_error(void);
+
+/* Create the per-GPU state of one sampler: p parameters, k observations (enka.__init__,
+ * ces/calibrate.py:14-22), J_local particle columns on this rank out of J_global, rank/nranks of the
+ * column sharding (1 GPU: J_local = J_global, rank 0 of 1).  With nranks > 1 every rank must use the
+ * same J_local (pad the last shard with zero columns and pass its true width to the phases through
+ * `cols_local`).  `stream` is a cudaStream_t (NULL = legacy default stream).  `d_panel_bytes` bounds the
+ * workspace of the J x J interaction matrix, which is formed in column panels (0 = 8 GiB default). */
+int ces_create(int64_t p, int64_t k, int64_t J_local, int64_t J_global, int rank, int nranks, int64_t cols_local,
+               void* stream, int64_t d_panel_bytes, ces_handle_t* out);
+int ces_destroy(ces_handle_t h);
+
+/* Problem data, HOST pointers, copied and factorised once (the reference re-solves with Gamma three
+ * times per step, ces/calibrate.py:429,434,435): y (k), Gamma (k x k, SPD, ld = k), Sigma0 = sampler.sigma
+ * (p x p, SPD, ld = p), mu (p), ustar (p).  Diagonal Gamma / Sigma0 are detected and take the scaling
+ * path.  Returns CES_ERR_NOT_SPD when a factorisation fails. */
+int ces_set_problem(ces_handle_t h, const double* y_host, const double* Gamma_host, const double* Sigma0_host,
+                    const double* mu_host, const double* ustar_host);
+
+/* ---- the update, in phases (single GPU: call them back to back, or use ces_step) ------------------
+ * phase 1  local row sums of G and U over the local particles -> sums_dev (k + p doubles)
+ *          [host: all-reduce(sum) of ces_buffer("sums")]
+ * phase 2  centring E, R, W = Gamma^-1 R, U~, Z = Sigma0^-1 (U - mu); local partial sums of the four
+ *          diagnostics; local partial covariance U~ U~^T
+ *          [host: all-reduce(sum) of "cuu"; all-gather of "e_all" and "ut_all" (rank-major blocks)]
+ * phase 3  chol(C^uu); D = (1/J) E^T W by source block and column panel with sum of squares; V = U~ D
+ *          [host: all-reduce(sum) of the first 5 doubles of "scalars"]
+ * phase 4a (aldi_constant only) drift and its local max-abs  [host: all-reduce(max) of scalars[5]]
+ * phase 4  step size, prior term, noise term, assembly of U_{n+1}; returns hk and the four diagnostics
+ *          (self-bias, bias, self-bias-data, bias-data: ces/calibrate.py:432-435) on the host.
+ * U, G, xi, U_out are device pointers to this rank's columns with leading dimensions ld*.  */
+int ces_phase1_sums(ces_handle_t h, const double* U_dev, int64_t ldu, const double* G_dev, int64_t ldg);
+int ces_phase2_centre(ces_handle_t h, int rule, const double* U_dev, int64_t ldu, const double* G_dev, int64_t ldg);
+int ces_phase3_interact(ces_handle_t h, int rule);
+int ces_phase4a_drift(ces_handle_t h, double switch_);
+int ces_phase4_update(ces_handle_t h, int rule, int ts_kind, double fixed_h, const double* U_dev, int64_t ldu,
+                      const double* xi_dev, int64_t ldxi, double* Uout_dev, int64_t ldo, double* hk_host,
+                      double* metrics_host /* [4] */);
+
+/* One whole single-GPU step on device buffers (nranks must be 1). */
+int ces_step(ces_handle_t h, int rule, int ts_kind, double fixed_h, double switch_, const double* U_dev, int64_t ldu,
+             const double* G_dev, int64_t ldg, const double* xi_dev, int64_t ldxi, double* Uout_dev, int64_t ldo,
+             double* hk_host, double* metrics_host);
+
+/* The same step on HOST buffers (dense, ld = J): host->device copies of U, G, xi and the device->host
+ * copy of U_out happen inside the call.  This is the call behind sampling.eks_update*(numpy arrays). */
+int ces_step_host(ces_handle_t h, int rule, int ts_kind, double fixed_h, double switch_, const double* U_host,
+                  const double* G_host, const double* xi_host, double* Uout_host, double* hk_host,
+                  double* metrics_host);
+
+/* Batched forward map G[:, j] = model(U[:, j]) for this rank's columns (enka.G_ens, ces/calibrate.py:106-130).
+ * CES_MAP_LINEAL / _LOG: A_dev is k x p (ld = lda, even, 16-byte aligned), b_dev is k doubles or NULL.
+ * CES_MAP_ELLIPTIC / _BANANA: params_host holds the two scalars named above, A_dev/b_dev are NULL. */
+int ces_forward_map(ces_handle_t h, int map_kind, const double* A_dev, int64_t lda, const double* b_dev,
+                    const double* params_host, const double* U_dev, int64_t ldu, double* G_dev, int64_t ldg);
+
+/* Named device buffers of the handle, for the host-side collectives and for tests:
+ * "sums" (k+p), "cuu" (p x ldp), "e_all" (nranks x k x ldJ), "ut_all" (nranks x p x ldJ), "scalars" (16),
+ * "w" (k x ldJ), "v" (p x ldJ), "chol" (p x ldp), "d_panel".  rows/cols/ld may be NULL. */
+int ces_buffer(ces_handle_t h, const char* name, double** ptr_dev, int64_t* rows, int64_t* cols, int64_t* ld);
+
+/* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
+int64_t ces_launch_count(ces_handle_t h);
+
+/* ---- building blocks exported for tests and for callers that own their orchestration ---------------
+ * C[M,N] = alpha * op(A) op(B) + beta * C on the FP64 tensor cores.  a_mode: 0 = A is M x K row-major,
+ * 1 = A is stored K x M (i.e. A^T given); b_mode: 0 = B is K x N row-major, 1 = B stored N x K.
+ * Operands need 16-byte aligned bases and even leading dimensions. */
+int ces_gemm(void* stream, int a_mode, int b_mode, int64_t M, int64_t N, int64_t K, double alpha, const double* A_dev,
+             int64_t lda, const double* B_dev, int64_t ldb, double beta, double* C_dev, int64_t ldc);
+/* In-place lower Cholesky of an n x n SPD matrix on the device (strict upper triangle zeroed). */
+int ces_potrf(void* stream, double* A_dev, int64_t ld, int64_t n);
+/* X = A^-1 B for SPD A (n x n) and B (n x nrhs), both on the device; A is overwritten by its factor. */
+int ces_posv(void* stream, double* A_dev, int64_t lda, int64_t n, double* B_dev, int64_t ldb, int64_t nrhs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CES_B200_H */
