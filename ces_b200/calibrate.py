@@ -1,0 +1,403 @@
+"""``enka`` / ``sampling`` with the call signatures of ``ces/calibrate.py``, running the
+ensemble Kalman update on a B200 through libces_b200.so.
+
+Drop-in for the numpy update: same constructor, same user-set attributes
+(``ustar, mu, sigma, T, parallel, mute_bar, directory, nexp``;
+examples/scripts/darcy-flow.py:65-83), same ``run`` / ``eks_update*`` /
+``timestep_method`` / ``G`` / ``G_ens`` / ``save`` / ``load`` signatures and the same
+result attributes (``Uall, Gall, Ustar, Gstar, metrics, radspec, online_path``;
+ces/calibrate.py:404-416).  What differs is where the arithmetic runs:
+
+* ``eks_update*`` take and return numpy arrays like the reference; the copies to
+  and from the device are inside the call (``ces_step_host``).
+* ``run`` keeps the ensemble resident in HBM between iterations.  Forward models
+  that carry a ``device_kind`` (``ces_b200.utils``, ``ces_b200.darcy``) are evaluated
+  for the whole ensemble on the device; any other ``model.type == 'map'`` callable is
+  evaluated particle by particle on the host exactly as ``enka.G_ens`` does
+  (ces/calibrate.py:106-130) -- that is the user's model, not a fallback of ours.
+* Noise: by default ``xi = np.random.normal(0, 1, [p, J])`` is drawn from the global
+  numpy RNG at the point where the reference draws it (ces/calibrate.py:447,488,527),
+  so a seeded script consumes the same random stream.
+* Multi-GPU: if ``self.group`` is a ``torch.distributed`` process group, every rank
+  calls ``run`` with the same arguments and the ensemble is sharded by particle
+  columns.
+
+There is no CPU implementation of the update in this package: without the CUDA
+library or without a GPU these classes raise.
+"""
+from __future__ import print_function
+
+import multiprocessing
+import os
+import pickle
+
+import numpy as np
+
+from .engine import Engine, shard_range
+
+_METRIC_KEYS = ("self-bias", "self-bias-data", "bias-data", "bias", "t")
+_RULE_METHOD = {"eks": "eks_update", "aldi": "eks_update_aldi", "aldi_constant": "eks_update_aldi_constant",
+                "eki": "eki_update"}
+
+
+def _fingerprint(a):
+    """Cheap identity of a problem array: object id, shape and a strided checksum.  Used to decide
+    whether the factorised problem data on the device is still current."""
+    a = np.asarray(a)
+    flat = a.reshape(-1)
+    stride = max(1, flat.shape[0] // 4096)
+    return (id(a), a.shape, float(flat[::stride].sum()))
+
+
+class enka(object):
+    """State holder of an ensemble Kalman run.  ces/calibrate.py:12-237."""
+
+    def __init__(self, p, n_obs, J):
+        self.n_obs = n_obs          # dimension of the observations
+        self.p = p                  # dimension of the parameters
+        self.J = J                  # ensemble size
+        self.epsilon = 1e-7
+        self.T = 30                 # maximum number of iterations
+        self.num_cores = multiprocessing.cpu_count()
+        self.parallel = False
+        self.mute_bar = True
+        self._engine = None
+        self._engine_key = None
+        self._problem_key = None
+
+    # ------------------------------------------------------------------ printing
+    def __repr__(self):
+        return "enka-%s-%s" % (str(self.J).zfill(4), getattr(self, "_update_name", "eks"))
+
+    def __str__(self):
+        print(r'Number of parameters ................. %s' % (self.p))
+        print(r'Dimension of forward model output .... %s' % (self.n_obs))
+        print(r'Ensemble size ........................ %s' % (self.J))
+        print(r'Evaluate G in parallel ............... %s' % (self.parallel))
+        print(r'Number of iterations to be run ....... %s' % (self.T))
+        if not hasattr(self, "directory"):
+            self.directory = os.getcwd()
+        print('Path to save: ......................... %s' % ('~/.../' + '/'.join(self.directory.split('/')[-2:])))
+        if hasattr(self, "Uall"):
+            print(r'Number of iterations EKS has run ..... %s' % (len(self.Uall) - 1))
+        else:
+            print(r'NOTE: EKS has not been run!')
+        return str()
+
+    # ------------------------------------------------------------------ stubs kept for API parity
+    def run(self, y_obs, U0, model, Gamma, Jnoise):
+        """Placeholder in the reference (ces/calibrate.py:50-68); ``sampling.run`` is the algorithm."""
+        pass
+
+    def run_sde(self, y_obs, U0, model, Gamma, Jnoise):
+        """Placeholder in the reference (ces/calibrate.py:70-87)."""
+        pass
+
+    # ------------------------------------------------------------------ forward evaluation
+    def G(self, theta, model):
+        """One particle through the forward model (ces/calibrate.py:95-104)."""
+        return model(theta)
+
+    def G_ens(self, theta, model):
+        """Forward model for a (p, N) collection of particles -> (n_obs, N)  (ces/calibrate.py:106-130).
+
+        Device maps run as one batched call on the GPU; other callables keep the reference's
+        per-particle host protocol (joblib when ``self.parallel``)."""
+        theta = np.asarray(theta, dtype=np.float64)
+        if self._is_device_model(model):
+            import torch
+
+            n = theta.shape[1]
+            if n == 0:
+                return np.zeros((self.n_obs, 0))
+            width = max(n, 2)                      # a handle needs at least two particles
+            padded = np.empty((theta.shape[0], width))
+            padded[:, :n] = theta
+            padded[:, n:] = theta[:, -1:]
+            eng = Engine(theta.shape[0], self.n_obs, width)
+            try:
+                U = torch.from_numpy(padded).cuda()
+                G = torch.empty(self.n_obs, width, dtype=torch.float64, device="cuda")
+                model.evaluate_ensemble(eng, U, G)
+                return G[:, :n].cpu().numpy()
+            finally:
+                eng.close()
+        return self._host_G_ens(theta, model)
+
+    def _host_G_ens(self, theta, model):
+        if self.parallel:
+            from joblib import Parallel, delayed
+
+            cols = Parallel(n_jobs=self.num_cores)(delayed(self.G)(col, model) for col in theta.T)
+            return np.asarray(cols).T
+        out = np.zeros((self.n_obs, theta.shape[1]))
+        for j, col in enumerate(theta.T):
+            out[:, j] = model(col)
+        return out
+
+    @staticmethod
+    def _is_device_model(model):
+        return getattr(model, "device_kind", None) is not None and not getattr(model, "flag_noise", False)
+
+    # ------------------------------------------------------------------ persistence (ces/calibrate.py:170-237)
+    def save(self, path='./', file='ces/', all=False, reset=True, online=False, counter=0):
+        """Same files as the reference: ``ensemble.npy``, ``Gensemble.npy``, ``metrics.pkl``
+        (+ ``*_path.npy`` with ``all``), or ``ensemble_NNNN.npy`` / ``Gensemble_NNNN.npy`` online."""
+        try:
+            os.makedirs(path + file)
+        except OSError:
+            pass
+        if not hasattr(self, "Uall"):
+            print('There is nothing to save')
+            return
+        if online:
+            np.save(path + file + 'ensemble_' + str(counter).zfill(4), self.Uall[-1])
+            np.save(path + file + 'Gensemble_' + str(counter).zfill(4), self.Gall[-1])
+        else:
+            np.save(path + file + 'ensemble', self.Ustar)
+            np.save(path + file + 'Gensemble', self.Gstar)
+            if all:
+                np.save(path + file + 'ensemble_path', self.Uall)
+                np.save(path + file + 'Gensemble_path', self.Gall)
+        with open(path + file + 'metrics.pkl', "wb") as fh:
+            pickle.dump(self.metrics, fh)
+
+    def load(self, path='./', eks_dir='ces/', ix_ensemble=False, flag_metrics=False):
+        """Rebuild ``Uall, Gall, Ustar, Gstar, J, metrics`` from a directory written by ``save``."""
+        where = path + eks_dir
+        try:
+            with open(where + 'metrics.pkl', 'rb') as fh:
+                self.metrics = pickle.load(fh)
+        except FileNotFoundError:
+            print('Metrics object not found. Could not load EKS object.')
+            return False
+        if not ix_ensemble:
+            try:
+                self.Uall = np.load(where + 'ensemble_path.npy')
+                self.Gall = np.load(where + 'Gensemble_path.npy')
+            except FileNotFoundError:
+                print('EKS trajectory files not found.')
+                return False
+            return True
+        if flag_metrics:
+            count = len(self.metrics['self-bias'])
+        else:
+            count = sum(1 for name in os.listdir(where) if name.split('_')[0] == 'ensemble')
+        try:
+            Us = [np.load(where + 'ensemble_' + str(i).zfill(4) + '.npy') for i in range(count)]
+            Gs = [np.load(where + 'Gensemble_' + str(i).zfill(4) + '.npy') for i in range(count)]
+        except FileNotFoundError:
+            return False
+        self.Uall, self.Gall = np.asarray(Us), np.asarray(Gs)
+        self.Ustar, self.Gstar = self.Uall[-1], self.Gall[-1]
+        self.J = self.Uall.shape[-1]
+        return True
+
+    # ------------------------------------------------------------------ device plumbing
+    def _get_engine(self, J, group=None):
+        key = (self.p, self.n_obs, int(J), id(group))
+        if self._engine is None or self._engine_key != key:
+            if self._engine is not None:
+                self._engine.close()
+            self._engine = Engine(self.p, self.n_obs, int(J), group=group,
+                                  d_panel_bytes=int(getattr(self, "d_panel_bytes", 0)))
+            self._engine_key = key
+            self._problem_key = None
+        return self._engine
+
+    def _sync_problem(self, eng, y_obs, Gamma):
+        # AttributeError when mu / sigma / ustar are unset, like the reference (:433, :443)
+        mu, sigma, ustar = self.mu, self.sigma, self.ustar
+        key = tuple(_fingerprint(a) for a in (y_obs, Gamma, sigma, mu, ustar))
+        if key != self._problem_key:
+            eng.set_problem(y_obs, Gamma, sigma, mu, ustar)
+            self._problem_key = key
+
+
+class sampling(enka):
+    """Ensemble Kalman sampler (EKS / ALDI).  ces/calibrate.py:241-529."""
+
+    # ------------------------------------------------------------------ step-size rule
+    def timestep_method(self, D, Geval, y_obs, Gamma, Jnoise, **kwargs):
+        """hk from an explicit interaction matrix D (ces/calibrate.py:243-267), with the same cumulative
+        time bookkeeping in ``self.metrics['t']``.  The update methods below compute the same quantity on
+        the device without materialising D on the host; this entry point serves callers that own a D."""
+        kind = kwargs.get('time_step', None)
+        const = kwargs.get('delta_t', 1. / (self.T / 2))
+        if kind is None or (kind == 'mix' and (len(self.metrics['t']) == 0 or
+                                               self.metrics['t'][-1] < kwargs.get('spinup', 4.))):
+            hk = 1. / (self._frobenius(D) + 1e-8)
+        elif kind in ('constant', 'mix'):
+            hk = const
+        else:
+            raise NotImplementedError("time_step=%r: 'spectral' is outside the accelerated path and 'adaptive' "
+                                      "is undefined in the reference (ces/calibrate.py:255)" % (kind,))
+        self._advance_time(hk)
+        return hk
+
+    @staticmethod
+    def _frobenius(D):
+        import torch
+
+        return float(torch.linalg.matrix_norm(torch.from_numpy(np.ascontiguousarray(D, dtype=np.float64)).cuda()))
+
+    def _advance_time(self, hk):
+        # ces/calibrate.py:262-265 (first step <=> no time recorded yet)
+        t = self.metrics['t']
+        t.append(hk if len(t) == 0 else hk + t[-1])
+
+    def _ensure_metrics(self):
+        if not hasattr(self, 'metrics'):
+            self.radspec = []
+            self.metrics = dict((key, []) for key in _METRIC_KEYS)
+
+    def _step_options(self, kwargs):
+        kind = kwargs.get('time_step', None)
+        if kind is None:
+            return None
+        if kind in ('constant', 'mix', 'spectral', 'adaptive'):
+            raise NotImplementedError(
+                "time_step=%r needs the Gamma -> hk*C^pp + Gamma re-solve (ces/calibrate.py:439-441, 470-473), "
+                "scheduled after the default path (SURVEY.md section 8f rank 3)" % (kind,))
+        raise ValueError("unknown time_step %r" % (kind,))
+
+    # ------------------------------------------------------------------ single updates on numpy arrays
+    def _update_host(self, rule, y_obs, U0, Geval, Gamma, kwargs):
+        self._ensure_metrics()
+        fixed = self._step_options(kwargs)
+        U0 = np.asarray(U0, dtype=np.float64)
+        eng = self._get_engine(U0.shape[1])
+        self._sync_problem(eng, y_obs, Gamma)
+        xi = None
+        if rule != 'eki':
+            xi = self._draw_noise(U0.shape, kwargs)
+        Uk, hk, met = eng.step_host(rule, U0, np.asarray(Geval, dtype=np.float64)[:self.n_obs], xi, fixed_h=fixed,
+                                    switch=kwargs.get('switch', 1.))
+        self._record(met, hk)
+        return Uk
+
+    def _draw_noise(self, shape, kwargs):
+        xi = kwargs.get('xi', None)
+        if xi is not None:
+            return np.asarray(xi, dtype=np.float64)
+        return np.random.normal(0, 1, [shape[0], shape[1]])
+
+    def _record(self, met, hk):
+        for key in ('self-bias', 'bias', 'self-bias-data', 'bias-data'):
+            self.metrics[key].append(met[key])
+        self._advance_time(hk)
+
+    def eks_update(self, y_obs, U0, Geval, Gamma, iter, **kwargs):
+        """Semi-implicit EKS step (ces/calibrate.py:418-449)."""
+        self.update_rule = 'eks_update'
+        return self._update_host('eks', y_obs, U0, Geval, Gamma, kwargs)
+
+    def eks_update_aldi(self, y_obs, U0, Geval, Gamma, iter, **kwargs):
+        """ALDI step, the default (ces/calibrate.py:451-490)."""
+        self.update_rule = 'eks_update_linear'
+        return self._update_host('aldi', y_obs, U0, Geval, Gamma, kwargs)
+
+    def eks_update_aldi_constant(self, y_obs, U0, Geval, Gamma, iter, **kwargs):
+        """ALDI step with h = 0.1 / max|drift| (ces/calibrate.py:492-529)."""
+        self.update_rule = 'eks_update_aldi'
+        return self._update_host('aldi_constant', y_obs, U0, Geval, Gamma, kwargs)
+
+    def eki_update(self, y_obs, U0, Geval, Gamma, iter, **kwargs):
+        """Deterministic ensemble Kalman inversion step U - h (U - ubar) D: the part every EKS rule shares
+        (first two terms of ces/calibrate.py:444 / :484).  The reference ships no EKI class."""
+        self.update_rule = 'eki_update'
+        return self._update_host('eki', y_obs, U0, Geval, Gamma, kwargs)
+
+    # ------------------------------------------------------------------ the run loop
+    def run(self, y_obs, U0, model, Gamma, Jnoise, save_online=False, trace=True, **kwargs):
+        """Ensemble Kalman sampler loop (ces/calibrate.py:270-416): forward -> trace -> update -> (save) ->
+        stop when the cumulative pseudo-time exceeds ``t_tol`` (default 2.0) or after ``self.T`` iterations.
+        ``Jnoise`` is accepted and ignored like in the reference (it recomputes cholesky(Gamma), :437)."""
+        import torch
+
+        mtype = model.type          # AttributeError if absent, like :294-297
+        if not hasattr(self, 'directory'):
+            self.directory = os.getcwd()
+        rule = kwargs.get('update', 'aldi')
+        self._update_name = rule
+        if mtype == 'pde':
+            raise NotImplementedError("'pde'-type forward models (ces/calibrate.py:132-168) are outside the "
+                                      "accelerated path this round (SURVEY.md section 8f rank 2)")
+        if mtype != 'map':
+            raise ValueError("model.type must be 'map' or 'pde'")
+        fixed = self._step_options(kwargs)
+        group = getattr(self, 'group', None)
+
+        U0 = np.ascontiguousarray(U0, dtype=np.float64)
+        J = U0.shape[1]
+        eng = self._get_engine(J, group)
+        self._sync_problem(eng, y_obs, Gamma)
+        lo, hi = eng.col_lo, eng.col_hi
+        dev = torch.device("cuda", torch.cuda.current_device())
+
+        if trace:
+            self.Uall = list(getattr(self, 'Uall', []))
+            self.Gall = list(getattr(self, 'Gall', []))
+        self._ensure_metrics()
+
+        U_dev = torch.from_numpy(U0[:, lo:hi].copy()).to(dev)
+        device_model = self._is_device_model(model)
+        G_dev = torch.empty(self.n_obs, hi - lo, dtype=torch.float64, device=dev)
+        known = rule in _RULE_METHOD
+
+        def forward(U_dev):
+            if device_model:
+                model.evaluate_ensemble(eng, U_dev, G_dev)
+                return G_dev, None
+            G_host = self._host_G_ens(U_dev.cpu().numpy(), model)
+            G_dev.copy_(torch.from_numpy(np.ascontiguousarray(G_host[:self.n_obs])))
+            return G_dev, G_host
+
+        def gather_host(local, rows):
+            """Full (rows, J) host array from the column shards."""
+            if eng.nranks == 1:
+                return local.cpu().numpy()
+            parts = [torch.empty(rows, eng.Jl, dtype=torch.float64, device=dev) for _ in range(eng.nranks)]
+            padded = torch.zeros(rows, eng.Jl, dtype=torch.float64, device=dev)
+            padded[:, :hi - lo] = local
+            eng.dist.all_gather(parts, padded, group=group)
+            full = torch.cat(parts, dim=1)[:, :J]
+            return full.cpu().numpy()
+
+        for i in range(self.T):
+            G_cur, G_host = forward(U_dev)
+            if trace:
+                self.Uall.append(gather_host(U_dev, self.p))
+                self.Gall.append(G_host if (G_host is not None and eng.nranks == 1) else gather_host(G_cur, self.n_obs))
+            if known:
+                setattr(self, 'update_rule', {'eks': 'eks_update', 'aldi': 'eks_update_linear',
+                                              'aldi_constant': 'eks_update_aldi', 'eki': 'eki_update'}[rule])
+                xi_dev = None
+                if rule != 'eki':
+                    xi = self._draw_noise((self.p, J), kwargs)          # same stream on every rank
+                    xi_dev = torch.from_numpy(np.ascontiguousarray(xi[:, lo:hi])).to(dev)
+                U_dev, hk, met = eng.step(rule, U_dev, G_cur, xi_dev, fixed_h=fixed, switch=kwargs.get('switch', 1.))
+                self._record(met, hk)
+            # an unknown ``update`` leaves the ensemble unchanged and records nothing, like :364-369 --
+            # the reference then fails on the empty ``metrics['t']``; so do we
+            if save_online:
+                tag = model.model_name + '-eks-' + str(model.l_window).zfill(3) + '-' + str(self.J).zfill(4)
+                if hasattr(self, 'nexp'):
+                    tag += '-' + str(self.nexp).zfill(2)
+                if eng.rank == 0:
+                    self.save(path=self.directory + '/ensembles/', file=tag + '/', online=True, counter=i)
+            if self.metrics['t'][-1] > kwargs.get('t_tol', 2.):
+                break
+
+        G_cur, G_host = forward(U_dev)
+        U_fin = gather_host(U_dev, self.p)
+        G_fin = G_host if (G_host is not None and eng.nranks == 1) else gather_host(G_cur, self.n_obs)
+        if trace:
+            self.Uall.append(U_fin)
+            self.Gall.append(G_fin)
+            self.Uall = np.asarray(self.Uall)
+            self.Gall = np.array(self.Gall)
+        self.Ustar = U_fin
+        self.Gstar = G_fin[:self.n_obs, :]
+        tail = '-' + str(self.J).zfill(4) + ('-' + str(self.nexp).zfill(2) if hasattr(self, 'nexp') else '') + '/'
+        self.online_path = self.directory + '/ensembles/' + model.model_name + tail

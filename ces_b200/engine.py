@@ -26,6 +26,39 @@ def shard_range(J, rank, nranks):
     return lo, min(J, lo + w)
 
 
+def run_sharded_phases(phases, buffer, dist, group, rank, p, k, rule):
+    """The collectives between the phases of one column-sharded update (include/ces_b200.h):
+
+        sums      -> all-reduce(sum)  "sums"  (k + p doubles)            means of G and U
+        centre    -> all-reduce(sum)  "cuu"   (p x ldp)                  C^uu from the local U~ U~^T
+                     all-gather       "e_all", "ut_all" (rank-major)     every rank needs all of E and U~
+        interact  -> all-reduce(sum)  "scalars"[0:5]                     ||D||_F^2 and the four diagnostics
+        drift     -> all-reduce(max)  "scalars"[5:6]                     aldi_constant only
+        update
+
+    ``phases`` maps those names to callables, ``buffer(name)`` returns the torch tensor the collective
+    runs on.  The engine passes the ctypes calls; tests/test_multirank_gloo.py passes a numpy stand-in to
+    exercise this orchestration over gloo without a GPU."""
+    phases["sums"]()
+    dist.all_reduce(buffer("sums"), group=group)
+    phases["centre"]()
+    dist.all_reduce(buffer("cuu"), group=group)
+    e_all, ut_all = buffer("e_all"), buffer("ut_all")
+    dist.all_gather_into_tensor(e_all, e_all[rank * k:(rank + 1) * k].clone(), group=group)
+    dist.all_gather_into_tensor(ut_all, ut_all[rank * p:(rank + 1) * p].clone(), group=group)
+    phases["interact"]()
+    scal = buffer("scalars")
+    head = scal[0, 0:5].clone()
+    dist.all_reduce(head, group=group)
+    scal[0, 0:5] = head
+    if rule == "aldi_constant":
+        phases["drift"]()
+        top = scal[0, 5:6].clone()
+        dist.all_reduce(top, op=dist.ReduceOp.MAX, group=group)
+        scal[0, 5:6] = top
+    phases["update"]()
+
+
 class _DeviceView(object):
     """Zero-copy torch view of a library-owned device buffer (``__cuda_array_interface__``)."""
 
@@ -138,22 +171,15 @@ class Engine(object):
             _lib.check(lib.ces_step(h, r, ts, fh, float(switch), Up, ldu, Gp, ldg, Xp, ldx, Op, ldo,
                                     ctypes.byref(self._hk), self._met))
         else:
-            dist, grp = self.dist, self.group
-            _lib.check(lib.ces_phase1_sums(h, Up, ldu, Gp, ldg))
-            dist.all_reduce(self.buffer("sums"), group=grp)
-            _lib.check(lib.ces_phase2_centre(h, r, Up, ldu, Gp, ldg))
-            dist.all_reduce(self.buffer("cuu"), group=grp)
-            e_all, ut_all = self.buffer("e_all"), self.buffer("ut_all")
-            dist.all_gather_into_tensor(e_all, e_all[self.rank * self.k:(self.rank + 1) * self.k], group=grp)
-            dist.all_gather_into_tensor(ut_all, ut_all[self.rank * self.p:(self.rank + 1) * self.p], group=grp)
-            _lib.check(lib.ces_phase3_interact(h, r))
-            scal = self.buffer("scalars")
-            dist.all_reduce(scal[0, 0:5], group=grp)
-            if rule == "aldi_constant":
-                _lib.check(lib.ces_phase4a_drift(h, float(switch)))
-                dist.all_reduce(scal[0, 5:6], op=dist.ReduceOp.MAX, group=grp)
-            _lib.check(lib.ces_phase4_update(h, r, ts, fh, Up, ldu, Xp, ldx, Op, ldo,
-                                             ctypes.byref(self._hk), self._met))
+            phases = {
+                "sums": lambda: _lib.check(lib.ces_phase1_sums(h, Up, ldu, Gp, ldg)),
+                "centre": lambda: _lib.check(lib.ces_phase2_centre(h, r, Up, ldu, Gp, ldg)),
+                "interact": lambda: _lib.check(lib.ces_phase3_interact(h, r)),
+                "drift": lambda: _lib.check(lib.ces_phase4a_drift(h, float(switch))),
+                "update": lambda: _lib.check(lib.ces_phase4_update(h, r, ts, fh, Up, ldu, Xp, ldx, Op, ldo,
+                                                                   ctypes.byref(self._hk), self._met)),
+            }
+            run_sharded_phases(phases, self.buffer, self.dist, self.group, self.rank, self.p, self.k, rule)
         met = {key: float(self._met[i]) for i, key in enumerate(_METRIC_KEYS)}
         return out, float(self._hk.value), met
 

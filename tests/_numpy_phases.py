@@ -1,0 +1,111 @@
+"""numpy stand-in for the library phases of one column-sharded update (TEST DOUBLE).
+
+Implements, on CPU torch tensors, exactly the buffer contract of include/ces_b200.h ("sums", "cuu",
+"e_all", "ut_all", "scalars"; rank-major blocks, zero-padded shard columns) so that
+ces_b200.engine.run_sharded_phases -- the host orchestration of the collectives -- can be exercised
+with gloo and world_size 2 on a machine without a GPU.  It is never imported by the product.
+"""
+import numpy as np
+import torch
+
+
+class NumpyPhases(object):
+    def __init__(self, p, k, J, rank, nranks, y, Gamma, mu, Sigma0, ustar):
+        self.p, self.k, self.J, self.rank, self.nranks = p, k, J, rank, nranks
+        self.Jl = -(-J // nranks)
+        self.ldJ = (self.Jl + 15) // 16 * 16
+        self.ldp = (p + 15) // 16 * 16
+        lo = min(J, rank * self.Jl)
+        self.lo, self.hi = lo, min(J, lo + self.Jl)
+        self.cols = self.hi - self.lo
+        self.y, self.Gamma, self.mu, self.Sigma0, self.ustar = y, Gamma, mu.reshape(p, 1), Sigma0, ustar.reshape(p, 1)
+        self.buf = {
+            "sums": torch.zeros(1, k + p, dtype=torch.float64),
+            "cuu": torch.zeros(p, self.ldp, dtype=torch.float64),
+            "e_all": torch.zeros(nranks * k, self.ldJ, dtype=torch.float64),
+            "ut_all": torch.zeros(nranks * p, self.ldJ, dtype=torch.float64),
+            "scalars": torch.zeros(1, 16, dtype=torch.float64),
+        }
+
+    def buffer(self, name):
+        return self.buf[name]
+
+    def bind(self, rule, U, G, xi, switch=1.0):
+        self.rule, self.U, self.G, self.xi, self.switch = rule, U, G, xi, switch
+        return {"sums": self.sums, "centre": self.centre, "interact": self.interact, "drift": self.drift,
+                "update": self.update}
+
+    def sums(self):
+        s = np.concatenate([self.G.sum(axis=1), self.U.sum(axis=1)])
+        self.buf["sums"][0] = torch.from_numpy(s)
+
+    def centre(self):
+        p, k, c = self.p, self.k, self.cols
+        means = self.buf["sums"][0].numpy() / self.J
+        E = self.G - means[:k, None]
+        R = self.G - self.y[:, None]
+        self.W = np.linalg.solve(self.Gamma, R)
+        Ut = self.U - means[k:, None]
+        self.Z = np.linalg.solve(self.Sigma0, self.U - self.mu)
+        e_all, ut_all = self.buf["e_all"].numpy(), self.buf["ut_all"].numpy()
+        e_all[self.rank * k:(self.rank + 1) * k] = 0.0
+        e_all[self.rank * k:(self.rank + 1) * k, :c] = E
+        ut_all[self.rank * p:(self.rank + 1) * p] = 0.0
+        ut_all[self.rank * p:(self.rank + 1) * p, :c] = Ut
+        S = self.buf["scalars"][0].numpy()
+        S[1] = (Ut ** 2).sum()
+        S[2] = ((self.U - self.ustar) ** 2).sum()
+        S[3] = (np.einsum("ij,ij->j", E, np.linalg.solve(self.Gamma, E)) ** 2).sum()
+        S[4] = (np.einsum("ij,ij->j", R, self.W) ** 2).sum()
+        alpha = 1.0 / self.J if self.rule == "eks" else 1.0 / (self.J - 1)
+        C = alpha * (Ut @ Ut.T)
+        if self.rank == 0:
+            C = C + 1e-8 * np.eye(p)
+        cuu = self.buf["cuu"].numpy()
+        cuu[:] = 0.0
+        cuu[:, :p] = C
+
+    def interact(self):
+        p, k, c = self.p, self.k, self.cols
+        e_all, ut_all = self.buf["e_all"].numpy(), self.buf["ut_all"].numpy()
+        self.C = self.buf["cuu"].numpy()[:, :p].copy()
+        ssq = 0.0
+        V = np.zeros((p, c))
+        for s in range(self.nranks):
+            Es = e_all[s * k:(s + 1) * k, :self.Jl]
+            Uts = ut_all[s * p:(s + 1) * p, :self.Jl]
+            D = (Es.T @ self.W) / self.J
+            ssq += (D ** 2).sum()
+            V += Uts @ D
+        self.V = V
+        self.buf["scalars"][0, 0] = ssq
+
+    def drift(self):
+        p, c = self.p, self.cols
+        Ut = self.buf["ut_all"].numpy()[self.rank * p:(self.rank + 1) * p, :c]
+        alpha = (p + 1.0) / self.J
+        self.T = -self.V - self.C @ self.Z + self.switch * alpha * Ut
+        self.buf["scalars"][0, 5] = np.abs(self.T).max() if c else 0.0
+
+    def update(self):
+        p, c = self.p, self.cols
+        S = self.buf["scalars"][0].numpy()
+        Ut = self.buf["ut_all"].numpy()[self.rank * p:(self.rank + 1) * p, :c]
+        alpha = (p + 1.0) / self.J
+        if self.rule == "aldi_constant":
+            h = 0.1 / S[5]
+            out = self.U + h * self.T + np.sqrt(2 * h) * (np.linalg.cholesky(self.C) @ self.xi)
+        else:
+            h = 1.0 / (np.sqrt(S[0]) + 1e-8)
+            if self.rule == "aldi":
+                out = (self.U + h * alpha * Ut - h * self.V - h * (self.C @ self.Z)
+                       + np.sqrt(2 * h) * (np.linalg.cholesky(self.C) @ self.xi))
+            elif self.rule == "eki":
+                out = self.U - h * self.V
+            else:
+                M = self.Sigma0 + h * self.C
+                rhs = self.U - h * self.V + h * (self.C @ np.linalg.solve(self.Sigma0, self.mu))
+                out = self.Sigma0 @ np.linalg.solve(M, rhs) + np.sqrt(2 * h) * (np.linalg.cholesky(self.C) @ self.xi)
+        self.out, self.hk = out, h
+        self.metrics = {"self-bias": S[1] / self.J, "bias": S[2] / self.J, "self-bias-data": S[3] / self.J,
+                        "bias-data": S[4] / self.J}

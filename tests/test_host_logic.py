@@ -1,0 +1,99 @@
+"""Host-side logic of the drop-in classes that needs no GPU: sharding arithmetic, time bookkeeping,
+persistence format, loud failure without CUDA."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from ces_b200 import calibrate
+from ces_b200.engine import Engine, shard_range, shard_width
+
+no_cuda = not torch.cuda.is_available()
+
+
+@pytest.mark.parametrize("J,n", [(100, 1), (100, 8), (17, 2), (17, 4), (5, 8), (65536, 8)])
+def test_shards_partition_the_ensemble(J, n):
+    w = shard_width(J, n)
+    assert w * n >= J
+    cols = []
+    for r in range(n):
+        lo, hi = shard_range(J, r, n)
+        assert 0 <= hi - lo <= w
+        cols.extend(range(lo, hi))
+    assert cols == list(range(J))
+
+
+def test_time_bookkeeping_matches_reference_rule():
+    s = calibrate.sampling(2, 3, 10)
+    s._ensure_metrics()
+    assert set(s.metrics) == {"self-bias", "self-bias-data", "bias-data", "bias", "t"} and s.radspec == []
+    s._advance_time(0.5)
+    s._advance_time(0.25)
+    assert s.metrics["t"] == [0.5, 0.75]
+
+
+def test_unsupported_time_steps_are_refused_loudly():
+    s = calibrate.sampling(2, 3, 10)
+    for kind in ("constant", "mix", "spectral", "adaptive"):
+        with pytest.raises(NotImplementedError):
+            s._step_options({"time_step": kind})
+    with pytest.raises(ValueError):
+        s._step_options({"time_step": "bogus"})
+    assert s._step_options({}) is None
+
+
+def test_save_load_round_trip(tmp_path):
+    """File names and contents of enka.save / enka.load (ces/calibrate.py:170-237)."""
+    s = calibrate.sampling(2, 3, 4)
+    rng = np.random.default_rng(0)
+    s.Uall = rng.standard_normal((3, 2, 4))
+    s.Gall = rng.standard_normal((3, 3, 4))
+    s.Ustar, s.Gstar = s.Uall[-1], s.Gall[-1]
+    s.metrics = {"self-bias": [1.0, 2.0], "bias": [3.0, 4.0], "self-bias-data": [5.0, 6.0], "bias-data": [7.0, 8.0],
+                 "t": [0.1, 0.3]}
+    path = str(tmp_path) + "/"
+    s.save(path=path, file="ces/", all=True)
+    assert sorted(os.listdir(path + "ces/")) == ["Gensemble.npy", "Gensemble_path.npy", "ensemble.npy",
+                                                 "ensemble_path.npy", "metrics.pkl"]
+    assert pickle.load(open(path + "ces/metrics.pkl", "rb")) == s.metrics
+    r = calibrate.sampling(2, 3, 99)
+    assert r.load(path=path, eks_dir="ces/") is True
+    assert np.array_equal(r.Uall, s.Uall) and np.array_equal(r.Gall, s.Gall) and r.metrics == s.metrics
+    for i in range(3):
+        s.Uall_i = None
+        s.save(path=path, file="online/", online=True, counter=i)
+    r2 = calibrate.sampling(2, 3, 99)
+    assert r2.load(path=path, eks_dir="online/", ix_ensemble=True) is True
+    assert r2.J == 4 and r2.Uall.shape == (3, 2, 4)
+    assert calibrate.sampling(2, 3, 4).load(path=path, eks_dir="missing/") is False if os.path.isdir(path + "missing/") else True
+
+
+def test_model_type_is_required_like_the_reference():
+    s = calibrate.sampling(2, 3, 4)
+
+    class NoType(object):
+        pass
+
+    with pytest.raises(AttributeError):
+        s.run(np.zeros(3), np.zeros((2, 4)), NoType(), np.eye(3), None)
+
+
+@pytest.mark.skipif(not no_cuda, reason="checks the no-GPU failure mode")
+def test_product_fails_loudly_without_cuda():
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Engine(2, 3, 10)
+    s = calibrate.sampling(2, 3, 10)
+    s.mu, s.sigma, s.ustar = np.zeros((2, 1)), np.eye(2), np.zeros((2, 1))
+    with pytest.raises(RuntimeError):
+        s.eks_update_aldi(np.zeros(3), np.zeros((2, 10)), np.zeros((3, 10)), np.eye(3), 0)
+
+
+def test_product_never_imports_the_oracle():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for dirpath, _, files in os.walk(os.path.join(root, "ces_b200")):
+        for name in files:
+            if name.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, name)).read()
+                assert "import oracle" not in text and "from oracle" not in text, name

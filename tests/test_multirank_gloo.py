@@ -1,0 +1,57 @@
+"""world_size-2 (and 3) gloo test of the column-sharded orchestration (ces_b200.engine.run_sharded_phases)
+on CPU: the collectives between the phases, the rank-major gather layout and the zero-padded ragged last
+shard must reproduce the single-process oracle step.  The per-rank arithmetic is a numpy stand-in
+(tests/_numpy_phases.py); on the GPU the same orchestration drives libces_b200.so."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _worker(rank, world, port, rule, d, k, J, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from _numpy_phases import NumpyPhases
+        from ces_b200.engine import run_sharded_phases
+        from oracle import eks_oracle as eo
+
+        pr = eo.linear_gaussian_problem(d, k, J, dense_gamma=True)
+        ph = NumpyPhases(d, k, J, rank, world, pr["y"], pr["Gamma"], pr["mu"], pr["Sigma0"], pr["ustar"])
+        sl = slice(ph.lo, ph.hi)
+        phases = ph.bind(rule, pr["U0"][:, sl], pr["G"][:, sl], pr["xi"][:, sl])
+        run_sharded_phases(phases, ph.buffer, dist, None, rank, d, k, rule)
+        ref = eo.step(rule, pr["y"], pr["U0"], pr["G"], pr["Gamma"], pr["mu"], pr["Sigma0"], pr["ustar"], pr["xi"])
+        err = np.abs(ph.out - ref["Uk"][:, sl]).max() / np.abs(ref["Uk"]).max() if ph.cols else 0.0
+        herr = abs(ph.hk - ref["hk"]) / ref["hk"]
+        merr = max(abs(ph.metrics[m] - ref["metrics"][m]) / abs(ref["metrics"][m]) for m in ph.metrics)
+        q.put((rank, float(err), float(herr), float(merr)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,rule,J", [(2, "aldi", 37), (2, "aldi_constant", 40), (2, "eks", 33), (3, "aldi", 16),
+                                          (2, "eki", 21)])
+def test_sharded_orchestration_matches_single_process(world, rule, J):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + J) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, world, port, rule, 5, 7, J, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    got = sorted(q.get(timeout=10) for _ in range(world))
+    for rank, err, herr, merr in got:
+        assert err < 1e-12 and herr < 1e-12 and merr < 1e-12, (rank, err, herr, merr)
