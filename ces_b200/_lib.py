@@ -22,6 +22,7 @@ EXPORTS = (
     "ces_version", "ces_last_error", "ces_create", "ces_destroy", "ces_set_problem", "ces_phase1_sums",
     "ces_phase2_centre", "ces_phase3_interact", "ces_phase4a_drift", "ces_phase4_update", "ces_step",
     "ces_step_host", "ces_forward_map", "ces_buffer", "ces_launch_count", "ces_gemm", "ces_potrf", "ces_posv",
+    "ces_profile_enable", "ces_profile_read",
 )
 
 _i64, _int, _dbl, _vp = ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_void_p
@@ -66,6 +67,8 @@ def load():
     lib.ces_forward_map.argtypes = [_vp, _int, _dp, _i64, _dp, _dp, _dp, _i64, _dp, _i64]
     lib.ces_buffer.argtypes = [_vp, ctypes.c_char_p, ctypes.POINTER(_vp), ctypes.POINTER(_i64),
                                ctypes.POINTER(_i64), ctypes.POINTER(_i64)]
+    lib.ces_profile_enable.argtypes = [_vp, _int]
+    lib.ces_profile_read.argtypes = [_vp, ctypes.POINTER(_dbl), ctypes.POINTER(_i64), ctypes.POINTER(_dbl)]
     lib.ces_gemm.argtypes = [_vp, _int, _int, _i64, _i64, _i64, _dbl, _dp, _i64, _dp, _i64, _dbl, _dp, _i64]
     lib.ces_potrf.argtypes = [_vp, _dp, _i64, _i64]
     lib.ces_posv.argtypes = [_vp, _dp, _i64, _i64, _dp, _i64, _i64]

@@ -32,6 +32,11 @@ struct ces_handle_s {
     int* hinfo = nullptr;
     double *stage_U = nullptr, *stage_G = nullptr, *stage_xi = nullptr, *stage_out = nullptr;
     std::vector<void*> allocs;
+    // optional event timing of the D = E^T W launches
+    bool profile = false;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    double prof_flops = 0.0;
 };
 
 namespace {
@@ -185,6 +190,7 @@ int ces_destroy(ces_handle_t h) {
     if (!h) return CES_OK;
     cudaStreamSynchronize(h->st);
     for (void* ptr : h->allocs) cudaFree(ptr);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->hS) cudaFreeHost(h->hS);
     delete h;
     cudaGetLastError();
@@ -335,7 +341,20 @@ int ces_phase3_interact(ces_handle_t h, int rule) {
             if (npart + tiles > h->ssq_cap) return fail(CES_ERR_STATE, "phase3: partial-sum buffer too small%s", "");
             g1.ssq_partials = h->ssq_partials + npart;
             npart += tiles;
+            if (h->profile) {
+                while (h->ev_pool.size() < h->ev_used + 2) {
+                    cudaEvent_t e;
+                    CES_CUDA(cudaEventCreate(&e));
+                    h->ev_pool.push_back(e);
+                }
+                CES_CUDA(cudaEventRecord(h->ev_pool[h->ev_used], st));
+            }
             CES_TRY(gemm(st, g1));
+            if (h->profile) {
+                CES_CUDA(cudaEventRecord(h->ev_pool[h->ev_used + 1], st));
+                h->ev_used += 2;
+                h->prof_flops += 2.0 * (double)k * (double)g1.M * (double)g1.N;
+            }
             GemmCall g2;
             g2.a_mode = A_MK; g2.b_mode = B_KN;
             g2.M = (int)p; g2.N = (int)nc; g2.K = (int)h->Jl;
@@ -522,6 +541,31 @@ int ces_forward_map(ces_handle_t h, int map_kind, const double* A, int64_t lda, 
         return banana_map(st, U, ldu, cols, params[0], params[1], G, ldg);
     }
     return fail(CES_ERR_INVALID, "ces_forward_map: unknown map kind %s%lld", "", map_kind);
+}
+
+int ces_profile_enable(ces_handle_t h, int on) {
+    CES_TRY(valid(h, false));
+    h->profile = on != 0;
+    h->ev_used = 0;
+    h->prof_flops = 0.0;
+    return CES_OK;
+}
+
+int ces_profile_read(ces_handle_t h, double* gemm_d_ms, int64_t* launches, double* flops) {
+    CES_TRY(valid(h, false));
+    CES_CUDA(cudaStreamSynchronize(h->st));
+    double total = 0.0;
+    for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
+        float ms = 0.f;
+        CES_CUDA(cudaEventElapsedTime(&ms, h->ev_pool[i], h->ev_pool[i + 1]));
+        total += ms;
+    }
+    if (gemm_d_ms) *gemm_d_ms = total;
+    if (launches) *launches = (int64_t)(h->ev_used / 2);
+    if (flops) *flops = h->prof_flops;
+    h->ev_used = 0;
+    h->prof_flops = 0.0;
+    return CES_OK;
 }
 
 int ces_buffer(ces_handle_t h, const char* name, double** ptr, int64_t* rows, int64_t* cols, int64_t* ld) {

@@ -140,6 +140,16 @@ class Engine(object):
             self._views[name] = self.torch.as_tensor(view, device="cuda")
         return self._views[name]
 
+    def profile(self, on=True):
+        """Bracket every D = E^T W launch with CUDA events (see ces_profile_enable)."""
+        _lib.check(self.lib.ces_profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self):
+        """(summed ms, launches, algorithmic flops) of the D GEMM since the previous read."""
+        ms, n, fl = ctypes.c_double(), ctypes.c_int64(), ctypes.c_double()
+        _lib.check(self.lib.ces_profile_read(self.h, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(fl)))
+        return ms.value, n.value, fl.value
+
     def launch_count(self):
         return int(self.lib.ces_launch_count(self.h))
 

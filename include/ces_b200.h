@@ -124,6 +124,13 @@ int ces_buffer(ces_handle_t h, const char* name, double** ptr_dev, int64_t* rows
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 int64_t ces_launch_count(ces_handle_t h);
 
+/* Optional device-side timing of the dominant kernel, the D = (1/J) E^T W GEMM: when enabled, phase 3
+ * brackets every launch of it with CUDA events on the handle's stream.  ces_profile_read synchronises the
+ * stream and returns the summed duration (ms), the number of launches and their algorithmic flops
+ * (2 * k * rows * cols each) since the previous read. */
+int ces_profile_enable(ces_handle_t h, int on);
+int ces_profile_read(ces_handle_t h, double* gemm_d_ms, int64_t* launches, double* flops);
+
 /* ---- building blocks exported for tests and for callers that own their orchestration ---------------
  * C[M,N] = alpha * op(A) op(B) + beta * C on the FP64 tensor cores.  a_mode: 0 = A is M x K row-major,
  * 1 = A is stored K x M (i.e. A^T given); b_mode: 0 = B is K x N row-major, 1 = B stored N x K.
