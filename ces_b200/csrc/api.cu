@@ -19,7 +19,7 @@ struct ces_handle_s {
     double *y = nullptr, *ginv_diag = nullptr, *Ginv = nullptr, *mu = nullptr, *ustar = nullptr;
     double *sinv_diag = nullptr, *sig_diag = nullptr, *Sinv = nullptr, *Sigma0 = nullptr, *bprior = nullptr;
     // per-step workspace (device)
-    double *sums = nullptr, *cvec = nullptr, *zvec = nullptr, *S = nullptr, *qpart = nullptr, *rowscratch = nullptr;
+    double *sums = nullptr, *cvec = nullptr, *zvec = nullptr, *S = nullptr, *qpart = nullptr, *rowscratch = nullptr, *formpart = nullptr;
     double *E_all = nullptr, *W = nullptr, *R = nullptr, *Ut_all = nullptr, *Z = nullptr, *Y = nullptr, *V = nullptr, *T = nullptr;
     double *xi_pad = nullptr, *expU = nullptr;
     double *Cuu = nullptr, *L = nullptr, *Linv = nullptr, *M = nullptr, *Minv = nullptr, *cb = nullptr;
@@ -145,7 +145,8 @@ int ces_create(int64_t p, int64_t k, int64_t J_local, int64_t J_global, int rank
     h->ldD = panel;
 
     int s = CES_OK;
-    const int ny = centre_rows_blocks(p > k ? p : k);
+    const int nyk0 = form_row_blocks(k, h->ldJ), nyp0 = form_row_blocks(p, h->ldJ);
+    const int ny = nyk0 > nyp0 ? nyk0 : nyp0;
     const int64_t tiles_per_rank = ceil_div(J_local, GEMM_BM) * ceil_div(J_local, GEMM_BN) + ceil_div(J_local, GEMM_BM) * ceil_div(J_local, panel);
     h->ssq_cap = tiles_per_rank * nranks + 16;
     // SYRK split-K: fill ~2 waves of 148 SMs with (lower tiles) x splits CTAs.
@@ -163,7 +164,7 @@ int ces_create(int64_t p, int64_t k, int64_t J_local, int64_t J_global, int rank
 #define A_(ptr, n) if (s == CES_OK) s = dalloc(h, &h->ptr, (n))
     A_(y, k); A_(ginv_diag, k); A_(mu, p); A_(ustar, p); A_(sinv_diag, p); A_(sig_diag, p); A_(bprior, p);
     A_(sums, k + p); A_(cvec, k); A_(zvec, k); A_(S, S_COUNT); A_(cb, p);
-    A_(qpart, 2 * (int64_t)ny * h->ldJ); A_(rowscratch, (p > k ? p : k));
+    A_(qpart, 2 * (int64_t)ny * h->ldJ); A_(formpart, 2 * ceil_div(h->ldJ, 256) + 2); A_(rowscratch, (p > k ? p : k));
     A_(E_all, (int64_t)nranks * k * h->ldJ); A_(W, k * h->ldJ);
     A_(Ut_all, (int64_t)nranks * p * h->ldJ); A_(Z, p * h->ldJ); A_(V, p * h->ldJ); A_(T, p * h->ldJ);
     A_(Cuu, p * h->ldp); A_(L, p * h->ldp); A_(Linv, round_up(p, CHOL_NB) * kLinvLd);
@@ -284,13 +285,13 @@ int ces_phase2_centre(ces_handle_t h, int rule, const double* U, int64_t ldu, co
         CES_TRY(gemm(st, g));
         CES_TRY(matvec(st, h->Ginv, h->ldk, k, h->cvec, h->zvec));
     }
-    const int nyk = centre_rows_blocks(k), nyp = centre_rows_blocks(p);
+    const int nyk = form_row_blocks(k, ld), nyp = form_row_blocks(p, ld);
     CES_TRY(data_forms(st, E, h->W, ld, k, h->cvec, h->zvec, h->qpart));
-    CES_TRY(finish_forms(st, h->qpart, nyk, ld, cols, true, h->S + S_SELF_DATA));
+    CES_TRY(finish_forms(st, h->qpart, nyk, ld, cols, true, h->formpart, h->S + S_SELF_DATA));
     // --- parameters: U~, Z, parameter-space diagnostics
     CES_TRY(centre_u(st, U, ldu, p, cols, h->sums + k, invJ, h->mu, h->ustar, h->sigma_diag ? h->sinv_diag : nullptr, Ut,
                      h->sigma_diag ? h->Z : h->Y, ld, h->qpart));
-    CES_TRY(finish_forms(st, h->qpart, nyp, ld, cols, false, h->S + S_SELF_BIAS));
+    CES_TRY(finish_forms(st, h->qpart, nyp, ld, cols, false, h->formpart, h->S + S_SELF_BIAS));
     if (!h->sigma_diag) {
         GemmCall g;   // Z = Sigma0^-1 (U - mu)
         g.a_mode = A_MK; g.b_mode = B_KN;

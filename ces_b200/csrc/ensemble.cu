@@ -103,14 +103,15 @@ __global__ void __launch_bounds__(256) centre_u_kernel(const double* __restrict_
                                                        const double* __restrict__ sums, double inv_J,
                                                        const double* __restrict__ mu, const double* __restrict__ ustar,
                                                        const double* __restrict__ sinv_diag, double* __restrict__ Ut,
-                                                       double* __restrict__ Z, long long ldo, double* __restrict__ qpart) {
+                                                       double* __restrict__ Z, long long ldo, double* __restrict__ qpart,
+                                                       int rows_per_cta) {
     const long long j = 2 * ((long long)blockIdx.x * 256 + threadIdx.x);
     if (j >= ldo) return;
-    const int i0 = blockIdx.y * CENTRE_ROWS;
+    const int i0 = blockIdx.y * rows_per_cta;
     double qs0 = 0, qs1 = 0, qb0 = 0, qb1 = 0;
     const bool in0 = j < cols, in1 = j + 1 < cols;
-#pragma unroll
-    for (int r = 0; r < CENTRE_ROWS; ++r) {
+#pragma unroll 4
+    for (int r = 0; r < rows_per_cta; ++r) {
         const int i = i0 + r;
         if (i >= p) break;
         const double mean = sums[i] * inv_J, mui = mu[i], us = ustar[i];
@@ -138,15 +139,25 @@ __global__ void __launch_bounds__(256) centre_u_kernel(const double* __restrict_
     *reinterpret_cast<double2*>(q_bias + j) = make_double2(qb0, qb1);
 }
 
-int centre_rows_blocks(int64_t rows) { return (int)ceil_div(rows, CENTRE_ROWS); }
+// Rows handled by one CTA of the kernels that emit per-particle partial sums: enough CTAs for ~4 waves
+// of 148 SMs, and few enough row blocks that the partial-sum pass stays small.
+int form_rows_per_cta(int64_t rows, int64_t ld) {
+    const int64_t col_blocks = ceil_div(ld, 512);
+    int64_t target = 592 / col_blocks;
+    if (target < 1) target = 1;
+    int64_t rpc = round_up(ceil_div(rows, target), 8);
+    return (int)(rpc < 8 ? 8 : rpc);
+}
+int form_row_blocks(int64_t rows, int64_t ld) { return (int)ceil_div(rows, form_rows_per_cta(rows, ld)); }
 
 int centre_u(cudaStream_t st, const double* U, int64_t ldu, int64_t p, int64_t cols, const double* sums, double inv_J,
              const double* mu, const double* ustar, const double* sinv_diag, double* Ut, double* Z, int64_t ldo,
              double* qpart) {
     const bool vec = ((reinterpret_cast<uintptr_t>(U) & 15) == 0) && (ldu % 2 == 0);
-    dim3 grid((unsigned)ceil_div(ldo, 512), (unsigned)ceil_div(p, CENTRE_ROWS));
-    if (vec) centre_u_kernel<true><<<grid, 256, 0, st>>>(U, ldu, (int)p, cols, sums, inv_J, mu, ustar, sinv_diag, Ut, Z, ldo, qpart);
-    else     centre_u_kernel<false><<<grid, 256, 0, st>>>(U, ldu, (int)p, cols, sums, inv_J, mu, ustar, sinv_diag, Ut, Z, ldo, qpart);
+    const int rpc = form_rows_per_cta(p, ldo);
+    dim3 grid((unsigned)ceil_div(ldo, 512), (unsigned)ceil_div(p, rpc));
+    if (vec) centre_u_kernel<true><<<grid, 256, 0, st>>>(U, ldu, (int)p, cols, sums, inv_J, mu, ustar, sinv_diag, Ut, Z, ldo, qpart, rpc);
+    else     centre_u_kernel<false><<<grid, 256, 0, st>>>(U, ldu, (int)p, cols, sums, inv_J, mu, ustar, sinv_diag, Ut, Z, ldo, qpart, rpc);
     CES_LAUNCHED(1);
     return CES_OK;
 }
@@ -157,13 +168,14 @@ int centre_u(cudaStream_t st, const double* U, int64_t ldu, int64_t p, int64_t c
 // Partial sums over this CTA's rows -> qpart[2][gridDim.y][ld].
 __global__ void __launch_bounds__(256) data_forms_kernel(const double* __restrict__ E, const double* __restrict__ W,
                                                          long long ld, int k, const double* __restrict__ cvec,
-                                                         const double* __restrict__ zvec, double* __restrict__ qpart) {
+                                                         const double* __restrict__ zvec, double* __restrict__ qpart,
+                                                         int rows_per_cta) {
     const long long j = 2 * ((long long)blockIdx.x * 256 + threadIdx.x);
     if (j >= ld) return;
-    const int m0 = blockIdx.y * CENTRE_ROWS;
+    const int m0 = blockIdx.y * rows_per_cta;
     double qe0 = 0, qe1 = 0, qr0 = 0, qr1 = 0;
-#pragma unroll
-    for (int r = 0; r < CENTRE_ROWS; ++r) {
+#pragma unroll 4
+    for (int r = 0; r < rows_per_cta; ++r) {
         const int m = m0 + r;
         if (m >= k) break;
         const double2 e = *reinterpret_cast<const double2*>(E + (size_t)m * ld + j);
@@ -180,37 +192,52 @@ __global__ void __launch_bounds__(256) data_forms_kernel(const double* __restric
 
 int data_forms(cudaStream_t st, const double* E, const double* W, int64_t ld, int64_t k, const double* cvec,
                const double* zvec, double* qpart) {
-    dim3 grid((unsigned)ceil_div(ld, 512), (unsigned)ceil_div(k, CENTRE_ROWS));
-    data_forms_kernel<<<grid, 256, 0, st>>>(E, W, ld, (int)k, cvec, zvec, qpart);
+    const int rpc = form_rows_per_cta(k, ld);
+    dim3 grid((unsigned)ceil_div(ld, 512), (unsigned)ceil_div(k, rpc));
+    data_forms_kernel<<<grid, 256, 0, st>>>(E, W, ld, (int)k, cvec, zvec, qpart, rpc);
     CES_LAUNCHED(1);
     return CES_OK;
 }
 
-// out[0] = sum_j f(sum_y qpart[0][y][j]),  out[1] = sum_j f(sum_y qpart[1][y][j]),  j < cols,
-// f = identity (SQUARE=false) or square (SQUARE=true).  One CTA, fixed order -> deterministic.
+// part[0][b] = sum_{j in block b} f(sum_y qpart[0][y][j]), part[1][b] likewise for qpart[1]; j < cols;
+// f = identity (SQUARE=false) or square (SQUARE=true).  One column per thread, fixed order.
 template <bool SQUARE>
-__global__ void __launch_bounds__(1024) finish_forms_kernel(const double* __restrict__ qpart, int ny, long long ld,
-                                                            long long cols, double* __restrict__ out) {
+__global__ void __launch_bounds__(256) finish_forms_kernel(const double* __restrict__ qpart, int ny, long long ld,
+                                                           long long cols, double* __restrict__ part) {
     __shared__ double scratch[32];
+    const long long j = (long long)blockIdx.x * 256 + threadIdx.x;
     double a0 = 0.0, a1 = 0.0;
-    for (long long j = threadIdx.x; j < cols; j += 1024) {
+    if (j < cols) {
         double q0 = 0.0, q1 = 0.0;
         for (int y = 0; y < ny; ++y) {
             q0 += qpart[(size_t)y * ld + j];
             q1 += qpart[((size_t)ny + y) * ld + j];
         }
-        a0 += SQUARE ? q0 * q0 : q0;
-        a1 += SQUARE ? q1 * q1 : q1;
+        a0 = SQUARE ? q0 * q0 : q0;
+        a1 = SQUARE ? q1 * q1 : q1;
     }
+    const double t0 = block_sum(a0, scratch);
+    const double t1 = block_sum(a1, scratch);
+    if (threadIdx.x == 0) { part[blockIdx.x] = t0; part[gridDim.x + blockIdx.x] = t1; }
+}
+// out[0] = sum part[0][:], out[1] = sum part[1][:]  (one CTA, fixed order -> deterministic)
+__global__ void __launch_bounds__(256) finish_pair_kernel(const double* __restrict__ part, int n, double* __restrict__ out) {
+    __shared__ double scratch[32];
+    double a0 = 0.0, a1 = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) { a0 += part[i]; a1 += part[n + i]; }
     const double t0 = block_sum(a0, scratch);
     const double t1 = block_sum(a1, scratch);
     if (threadIdx.x == 0) { out[0] = t0; out[1] = t1; }
 }
 
-int finish_forms(cudaStream_t st, const double* qpart, int ny, int64_t ld, int64_t cols, bool square, double* out) {
-    if (square) finish_forms_kernel<true><<<1, 1024, 0, st>>>(qpart, ny, ld, cols, out);
-    else        finish_forms_kernel<false><<<1, 1024, 0, st>>>(qpart, ny, ld, cols, out);
-    CES_LAUNCHED(1);
+// `part` holds 2 * ceil(cols / 256) doubles of scratch.
+int finish_forms(cudaStream_t st, const double* qpart, int ny, int64_t ld, int64_t cols, bool square, double* part,
+                 double* out) {
+    const int nb = (int)ceil_div(cols < 1 ? 1 : cols, 256);
+    if (square) finish_forms_kernel<true><<<nb, 256, 0, st>>>(qpart, ny, ld, cols, part);
+    else        finish_forms_kernel<false><<<nb, 256, 0, st>>>(qpart, ny, ld, cols, part);
+    finish_pair_kernel<<<1, 256, 0, st>>>(part, nb, out);
+    CES_LAUNCHED(2);
     return CES_OK;
 }
 

@@ -55,10 +55,12 @@ int centre_g(cudaStream_t st, const double* G, int64_t ldg, int64_t k, int64_t c
 int centre_u(cudaStream_t st, const double* U, int64_t ldu, int64_t p, int64_t cols, const double* sums, double inv_J,
              const double* mu, const double* ustar, const double* sinv_diag, double* Ut, double* Z, int64_t ldo,
              double* qpart);
-int centre_rows_blocks(int64_t rows);
+int form_rows_per_cta(int64_t rows, int64_t ld);
+int form_row_blocks(int64_t rows, int64_t ld);
 int data_forms(cudaStream_t st, const double* E, const double* W, int64_t ld, int64_t k, const double* cvec,
                const double* zvec, double* qpart);
-int finish_forms(cudaStream_t st, const double* qpart, int ny, int64_t ld, int64_t cols, bool square, double* out);
+int finish_forms(cudaStream_t st, const double* qpart, int ny, int64_t ld, int64_t cols, bool square, double* part,
+                 double* out);
 int sum_vector(cudaStream_t st, const double* v, int64_t n, double* out);
 int matvec(cudaStream_t st, const double* M, int64_t ld, int64_t n, const double* x, double* y);
 int scale_vector(cudaStream_t st, const double* d, const double* x, double* y, int64_t n);
