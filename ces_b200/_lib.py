@@ -22,7 +22,7 @@ EXPORTS = (
     "ces_version", "ces_last_error", "ces_create", "ces_destroy", "ces_set_problem", "ces_phase1_sums",
     "ces_phase2_centre", "ces_phase3_interact", "ces_phase4a_drift", "ces_phase4_update", "ces_step",
     "ces_step_host", "ces_forward_map", "ces_buffer", "ces_launch_count", "ces_gemm", "ces_potrf", "ces_posv",
-    "ces_profile_enable", "ces_profile_read",
+    "ces_profile_enable", "ces_profile_read", "ces_darcy_create", "ces_darcy_destroy", "ces_darcy_forward",
 )
 
 _i64, _int, _dbl, _vp = ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_void_p
@@ -69,6 +69,9 @@ def load():
                                ctypes.POINTER(_i64), ctypes.POINTER(_i64)]
     lib.ces_profile_enable.argtypes = [_vp, _int]
     lib.ces_profile_read.argtypes = [_vp, ctypes.POINTER(_dbl), ctypes.POINTER(_i64), ctypes.POINTER(_dbl)]
+    lib.ces_darcy_create.argtypes = [_i64, _i64, _dp, _dp, _dp, _vp, _i64, _vp, ctypes.POINTER(_vp)]
+    lib.ces_darcy_destroy.argtypes = [_vp]
+    lib.ces_darcy_forward.argtypes = [_vp, _dp, _i64, _i64, _dp, _i64, _int, _dbl, _int, ctypes.POINTER(_int)]
     lib.ces_gemm.argtypes = [_vp, _int, _int, _i64, _i64, _i64, _dbl, _dp, _i64, _dp, _i64, _dbl, _dp, _i64]
     lib.ces_potrf.argtypes = [_vp, _dp, _i64, _i64]
     lib.ces_posv.argtypes = [_vp, _dp, _i64, _i64, _dp, _i64, _i64]

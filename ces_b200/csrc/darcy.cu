@@ -1,0 +1,388 @@
+// Batched 2-D Darcy forward solve, one thread-block cluster per ensemble member.
+//
+// Reference arithmetic: ces/darcy.py:20-38,84-98,129-138 -> utilities/mfiles/gaussrnd_coarse.m:6-23 (KL field by
+// inverse 2-D DCT) and utilities/mfiles/solve_gwf.m:4-39 (spline to the K x K nodes, 5-point finite differences with
+// arithmetic-mean face coefficients scaled by (K-1)^2, right-hand side 1, zero Dirichlet boundary, spline back to the
+// cell centres), one MATLAB-engine round trip per particle in the reference.
+//
+// Here, per chunk of members (all buffers member-major, a member's K x K field contiguous):
+//   Theta = U^T Phi^T                       DMMA GEMM (A_KM x B_KN)
+//   a     = exp(Theta)                      elementwise
+//   T1    = a S^T ; c_z = S T1_z            two DMMA GEMMs (stacked, then batched with the shared operand S)
+//   solve sum_faces w (p_i - p_nb) = h^2    darcy_pcg_kernel: Jacobi-preconditioned CG, the member's vectors live in
+//                                           registers + shared memory of a cluster of CTAs (row strips; halo rows are
+//                                           pushed into the neighbour's shared memory, dot products are combined through
+//                                           distributed shared memory)
+//   T2 = p S2^T ; P_z = S2 T2_z             spline back to the centres (two more GEMMs)
+//   G[o, member] = P_z[obs_index[o]]        gather (or the transposed full field)
+#include <cooperative_groups.h>
+#include <vector>
+#include "kernels.h"
+
+namespace cg = cooperative_groups;
+
+namespace ces {
+
+constexpr int PCG_THREADS = 512;   // one quad of 4 adjacent nodes per thread
+
+// Shared-memory layout of one CTA: c and p strips with one halo row above and below.
+struct PcgShared {
+    double red[2][2][8];   // [parity][which dot][cta rank] partial dot products (read by every CTA of the cluster)
+};
+
+__device__ __forceinline__ double block_sum_512(double v, double* scratch) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) scratch[wid] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < PCG_THREADS / 32; ++w) t += scratch[w];   // every thread sums in the same order
+    return t;
+}
+
+// One cluster (gridDim.x = members * C, cluster dims (C,1,1)) solves one member.
+//   cn  : nodal coefficient fields, member-major (K x K each)
+//   pn  : nodal pressure out (K x K each, boundary rows/cols zero)
+__global__ void __launch_bounds__(PCG_THREADS, 1)
+darcy_pcg_kernel(const double* __restrict__ cn, double* __restrict__ pn, int K, int R, double tol2, int max_iter,
+                 int* __restrict__ iters_out) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks();
+    const int crank = (int)cluster.block_rank();
+    const long long member = blockIdx.x / C;
+    extern __shared__ double smem[];
+    double* cs = smem;                              // (R + 2) x K  nodal coefficients, rows r0-1 .. r0+R
+    double* ps = cs + (size_t)(R + 2) * K;          // (R + 2) x K  search direction with halos
+    __shared__ PcgShared sh;
+    __shared__ double scratch[PCG_THREADS / 32];
+
+    const int r0 = 1 + crank * R;                   // first interior nodal row of this strip
+    const int quads = K >> 2;
+    const int qrow = threadIdx.x / quads, qcol = threadIdx.x % quads;
+    const int i = r0 + qrow, j0 = qcol * 4;
+    const bool active = qrow < R;                   // threads beyond the strip only take part in the barriers
+    const bool row_ok = active && (i <= K - 2);
+    const double* cfield = cn + (size_t)member * K * K;
+
+    // ---- load coefficient strip (with halos) and clear p
+    for (int idx = threadIdx.x; idx < (R + 2) * K; idx += PCG_THREADS) {
+        const int rr = r0 - 1 + idx / K;
+        cs[idx] = (rr <= K - 1) ? cfield[(size_t)rr * K + idx % K] : 0.0;
+        ps[idx] = 0.0;
+    }
+    __syncthreads();
+
+    // ---- per-node data in registers
+    double wN[4], wS[4], wWE[5], invd[4], x[4], r[4], p[4];
+    bool ok[4];
+    const double h2 = 1.0 / ((double)(K - 1) * (double)(K - 1));
+    {
+        const double* cm = cs + (size_t)((active ? qrow : 0) + 1) * K;     // own row
+        const double* cu = cm - K;                          // north
+        const double* cd = cm + K;                          // south
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int j = j0 + q;
+            ok[q] = row_ok && j >= 1 && j <= K - 2;
+            const double cc = row_ok ? cm[j] : 0.0;
+            wN[q] = row_ok ? 0.5 * (cu[j] + cc) : 0.0;
+            wS[q] = row_ok ? 0.5 * (cd[j] + cc) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {                       // face between columns j0+q-1 and j0+q
+            const int jl = j0 + q - 1, jr = j0 + q;
+            wWE[q] = (row_ok && jl >= 0 && jr <= K - 1) ? 0.5 * (cm[jl] + cm[jr]) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const double d = wN[q] + wS[q] + wWE[q] + wWE[q + 1];
+            invd[q] = ok[q] ? 1.0 / d : 0.0;
+            x[q] = 0.0;
+            r[q] = ok[q] ? h2 : 0.0;                        // b - A*0
+        }
+    }
+    // z = M^-1 r ; p = z ; rz = r.z
+    double rz_loc = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { p[q] = r[q] * invd[q]; rz_loc += r[q] * p[q]; }
+
+    double* prow = ps + (size_t)((active ? qrow : 0) + 1) * K + j0;
+    double* north_halo = nullptr;   // neighbour's south-halo row (we are its north... see below)
+    double* south_halo = nullptr;
+    if (crank > 0) north_halo = cluster.map_shared_rank(ps, crank - 1) + (size_t)(R + 1) * K;   // rank-1's bottom halo = our first row
+    if (crank < C - 1) south_halo = cluster.map_shared_rank(ps, crank + 1);                      // rank+1's top halo = our last row
+
+    auto publish_p = [&]() {
+        if (active) {
+            *reinterpret_cast<double2*>(prow) = make_double2(p[0], p[1]);
+            *reinterpret_cast<double2*>(prow + 2) = make_double2(p[2], p[3]);
+            if (qrow == 0 && north_halo) {
+                *reinterpret_cast<double2*>(north_halo + j0) = make_double2(p[0], p[1]);
+                *reinterpret_cast<double2*>(north_halo + j0 + 2) = make_double2(p[2], p[3]);
+            }
+            if (qrow == R - 1 && south_halo) {
+                *reinterpret_cast<double2*>(south_halo + j0) = make_double2(p[0], p[1]);
+                *reinterpret_cast<double2*>(south_halo + j0 + 2) = make_double2(p[2], p[3]);
+            }
+        }
+    };
+    int parity = 0;
+    // Cluster-wide sum: every CTA pushes its block partial into slot [crank] of every CTA (remote stores are
+    // fire-and-forget), one cluster barrier, then each thread adds the C local slots in rank order -- the same
+    // order on every CTA, so all of them take identical decisions.
+    auto cluster_dot = [&](double local, int which) -> double {
+        const double b = block_sum_512(local, scratch);
+        if ((int)threadIdx.x < C) cluster.map_shared_rank(&sh, threadIdx.x)->red[parity][which][crank] = b;
+        cluster.sync();
+        double t = 0.0;
+        for (int c = 0; c < C; ++c) t += sh.red[parity][which][c];
+        return t;
+    };
+
+    publish_p();
+    double rz = cluster_dot(rz_loc, 0);    // the sync inside also makes the halos of p visible
+    parity ^= 1;
+    const double rz0 = rz;
+    int it = 0;
+    if (rz0 > 0.0) {
+        for (it = 0; it < max_iter; ++it) {
+            // ---- ap = A p
+            double ap[4] = {0.0, 0.0, 0.0, 0.0}, pap_loc = 0.0;
+            if (active) {
+                const double2 n01 = *reinterpret_cast<const double2*>(prow - K), n23 = *reinterpret_cast<const double2*>(prow - K + 2);
+                const double2 s01 = *reinterpret_cast<const double2*>(prow + K), s23 = *reinterpret_cast<const double2*>(prow + K + 2);
+                const double pw = (j0 > 0) ? prow[-1] : 0.0;
+                const double pe = (j0 + 4 < K) ? prow[4] : 0.0;
+                const double pn_[4] = {n01.x, n01.y, n23.x, n23.y};
+                const double ps_[4] = {s01.x, s01.y, s23.x, s23.y};
+                const double pl[6] = {pw, p[0], p[1], p[2], p[3], pe};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double d = wN[q] + wS[q] + wWE[q] + wWE[q + 1];
+                    double v = d * p[q] - wN[q] * pn_[q] - wS[q] * ps_[q] - wWE[q] * pl[q] - wWE[q + 1] * pl[q + 2];
+                    ap[q] = ok[q] ? v : 0.0;
+                    pap_loc += p[q] * ap[q];
+                }
+            }
+            const double pap = cluster_dot(pap_loc, 0);
+            const double alpha = rz / pap;
+            double rz_new_loc = 0.0, z[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                x[q] += alpha * p[q];
+                r[q] -= alpha * ap[q];
+                z[q] = r[q] * invd[q];
+                rz_new_loc += r[q] * z[q];
+            }
+            const double rz_new = cluster_dot(rz_new_loc, 1);
+            parity ^= 1;
+            if (rz_new <= tol2 * rz0) { ++it; break; }
+            const double beta = rz_new / rz;
+            rz = rz_new;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) p[q] = z[q] + beta * p[q];
+            publish_p();
+            cluster.sync();      // new p and its halos visible everywhere before the next stencil
+        }
+    }
+    // ---- write the nodal pressure (boundary stays zero: the buffer is cleared beforehand)
+    if (row_ok) {
+        double* out = pn + (size_t)member * K * K + (size_t)i * K + j0;
+        *reinterpret_cast<double2*>(out) = make_double2(x[0], x[1]);
+        *reinterpret_cast<double2*>(out + 2) = make_double2(x[2], x[3]);
+    }
+    if (threadIdx.x == 0 && crank == 0) atomicMax(iters_out, it);
+    cluster.sync();              // no CTA may exit while a neighbour can still touch its shared memory
+}
+
+// G[o, col0 + m] = P[m, obs[o]]  (n_obs rows) -- or, with obs == nullptr, the full transposed field.
+__global__ void __launch_bounds__(256) darcy_gather_kernel(const double* __restrict__ P, long long cells, int members,
+                                                           const long long* __restrict__ obs, int rows,
+                                                           double* __restrict__ G, long long ldg) {
+    const int m = blockIdx.x * 256 + threadIdx.x;
+    const int o = blockIdx.y;
+    if (m >= members) return;
+    const long long cell = obs ? obs[o] : o;
+    G[(size_t)o * ldg + m] = P[(size_t)m * cells + cell];
+}
+
+struct DarcyModel {
+    int N = 0, p = 0, n_obs = 0, C = 1, R = 0;
+    int64_t chunk = 0;
+    cudaStream_t st = nullptr;
+    double *PhiT = nullptr, *S = nullptr, *S2 = nullptr, *B0 = nullptr, *B1 = nullptr, *B2 = nullptr, *Upad = nullptr;
+    long long* obs = nullptr;
+    int* iters = nullptr;
+    int64_t upad_cols = 0;
+};
+
+static int pcg_launch(DarcyModel* m, const double* cn, double* pn, int members, double tol, int max_iter) {
+    const int K = m->N;
+    const size_t smem = (size_t)2 * (m->R + 2) * K * sizeof(double);
+    static size_t configured = 0;
+    if (smem > configured) {
+        CES_CUDA(cudaFuncSetAttribute(darcy_pcg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(members * m->C));
+    cfg.blockDim = dim3(PCG_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = m->st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)m->C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CES_CUDA(cudaLaunchKernelEx(&cfg, darcy_pcg_kernel, cn, pn, K, m->R, tol * tol, max_iter, m->iters));
+    CES_LAUNCHED(1);
+    return CES_OK;
+}
+
+}  // namespace ces
+
+using namespace ces;
+
+extern "C" {
+
+int ces_darcy_create(int64_t N, int64_t p, const double* PhiT_host, const double* S_host, const double* S2_host,
+                     const int64_t* obs_host, int64_t n_obs, void* stream, void** out) {
+    if (!out) return fail(CES_ERR_INVALID, "ces_darcy_create: null output%s", "");
+    *out = nullptr;
+    if (N < 16 || N > 128 || N % 16 != 0 || p < 1 || p > N * N || !PhiT_host || !S_host || !S2_host || n_obs < 0 ||
+        (n_obs > 0 && !obs_host))
+        return fail(CES_ERR_INVALID, "ces_darcy_create: needs 16 <= N <= 128, N %% 16 == 0, 1 <= p <= N^2%s", "");
+    for (int64_t o = 0; o < n_obs; ++o)
+        if (obs_host[o] < 0 || obs_host[o] >= N * N) return fail(CES_ERR_INVALID, "ces_darcy_create: obs_index out of range%s", "");
+    DarcyModel* m = new DarcyModel();
+    m->N = (int)N; m->p = (int)p; m->n_obs = (int)n_obs;
+    m->st = static_cast<cudaStream_t>(stream);
+    // strip height: one quad (4 nodes) per thread -> R * N/4 <= PCG_THREADS; cluster size from {1,2,4,8}
+    const int quads = (int)N / 4;
+    int C = 1;
+    while (C < 8 && ((N - 2 + C - 1) / C) * quads > PCG_THREADS) C *= 2;
+    m->C = C;
+    m->R = (int)((N - 2 + C - 1) / C);
+    if ((int64_t)m->R * quads > PCG_THREADS) { delete m; return fail(CES_ERR_INVALID, "ces_darcy_create: grid too large%s", ""); }
+    const int64_t cells = N * N;
+    m->chunk = (1ll << 29) / (cells * 8);          // 512 MiB per field buffer
+    if (m->chunk > 32768) m->chunk = 32768;
+    if (m->chunk < 64) m->chunk = 64;
+    auto up = [&](double** dst, const double* src, int64_t n) -> int {
+        CES_CUDA(cudaMalloc(dst, n * sizeof(double)));
+        CES_CUDA(cudaMemcpyAsync(*dst, src, n * sizeof(double), cudaMemcpyHostToDevice, m->st));
+        return CES_OK;
+    };
+    int s = up(&m->PhiT, PhiT_host, p * cells);
+    if (s == CES_OK) s = up(&m->S, S_host, N * N);
+    if (s == CES_OK) s = up(&m->S2, S2_host, N * N);
+    if (s == CES_OK && n_obs > 0) {
+        if (cudaMalloc(&m->obs, n_obs * sizeof(long long)) != cudaSuccess) s = fail(CES_ERR_NOMEM, "cudaMalloc failed%s", "");
+        else if (cudaMemcpyAsync(m->obs, obs_host, n_obs * sizeof(long long), cudaMemcpyHostToDevice, m->st) != cudaSuccess)
+            s = fail(CES_ERR_CUDA, "obs upload failed%s", "");
+    }
+    if (s == CES_OK && cudaMalloc(&m->iters, sizeof(int)) != cudaSuccess) s = fail(CES_ERR_NOMEM, "cudaMalloc failed%s", "");
+    if (s == CES_OK && cudaStreamSynchronize(m->st) != cudaSuccess) s = fail(CES_ERR_CUDA, "ces_darcy_create: upload failed%s", "");
+    if (s != CES_OK) { ces_darcy_destroy(m); return s; }
+    *out = m;
+    return CES_OK;
+}
+
+int ces_darcy_destroy(void* handle) {
+    DarcyModel* m = static_cast<DarcyModel*>(handle);
+    if (!m) return CES_OK;
+    cudaStreamSynchronize(m->st);
+    cudaFree(m->PhiT); cudaFree(m->S); cudaFree(m->S2); cudaFree(m->B0); cudaFree(m->B1); cudaFree(m->B2);
+    cudaFree(m->Upad); cudaFree(m->obs); cudaFree(m->iters);
+    delete m;
+    cudaGetLastError();
+    return CES_OK;
+}
+
+int ces_darcy_forward(void* handle, const double* U, int64_t ldu, int64_t cols, double* G, int64_t ldg, int full_solution,
+                      double tol, int max_iter, int* iters_host) {
+    DarcyModel* m = static_cast<DarcyModel*>(handle);
+    if (!m || !U || !G || cols < 0 || ldu < cols || ldg < cols) return fail(CES_ERR_INVALID, "ces_darcy_forward: bad argument%s", "");
+    if (!full_solution && m->n_obs == 0) return fail(CES_ERR_STATE, "ces_darcy_forward: no obs_index was given%s", "");
+    if (cols == 0) return CES_OK;
+    const int N = m->N, p = m->p;
+    const int64_t cells = (int64_t)N * N;
+    cudaStream_t st = m->st;
+    if (tol <= 0.0) tol = 1e-13;
+    if (max_iter <= 0) max_iter = 40 * N;
+    const int64_t chunk = cols < m->chunk ? cols : m->chunk;
+    if (!m->B0) {
+        const size_t bytes = (size_t)m->chunk * cells * sizeof(double);
+        if (cudaMalloc(&m->B0, bytes) != cudaSuccess || cudaMalloc(&m->B1, bytes) != cudaSuccess ||
+            cudaMalloc(&m->B2, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(CES_ERR_NOMEM, "ces_darcy_forward: workspace allocation failed%s", "");
+        }
+    }
+    // the KL GEMM reads U^T through TMA: 16-byte aligned base and even pitch, else re-pack once
+    const double* Uuse = U;
+    int64_t ldu_use = ldu;
+    if ((reinterpret_cast<uintptr_t>(U) & 15) != 0 || (ldu & 1)) {
+        const int64_t ldp = padded_ld(cols);
+        if (m->upad_cols < ldp) {
+            cudaFree(m->Upad);
+            m->Upad = nullptr;
+            if (cudaMalloc(&m->Upad, (size_t)p * ldp * sizeof(double)) != cudaSuccess) return fail(CES_ERR_NOMEM, "cudaMalloc failed%s", "");
+            m->upad_cols = ldp;
+        }
+        CES_TRY(pad_copy(st, U, ldu, p, cols, m->Upad, ldp));
+        Uuse = m->Upad; ldu_use = ldp;
+    }
+    CES_CUDA(cudaMemsetAsync(m->iters, 0, sizeof(int), st));
+    for (int64_t c0 = 0; c0 < cols; c0 += chunk) {
+        const int64_t mc = (cols - c0) < chunk ? (cols - c0) : chunk;
+        if (c0 % 2 != 0) return fail(CES_ERR_ALIGN, "ces_darcy_forward: odd chunk offset%s", "");
+        // 1. Theta = U^T Phi^T  (mc x cells)
+        GemmCall g;
+        g.a_mode = A_KM; g.b_mode = B_KN;
+        g.M = (int)mc; g.N = (int)cells; g.K = p;
+        g.A = Uuse + c0; g.lda = ldu_use; g.B = m->PhiT; g.ldb = cells; g.C = m->B0; g.ldc = cells;
+        CES_TRY(gemm(st, g));
+        // 2. a = exp(Theta)
+        CES_TRY(exp_map(st, m->B0, cells, mc, cells, m->B0, cells));
+        // 3. T1 = a S^T (stacked rows), c_z = S T1_z
+        GemmCall t1;
+        t1.a_mode = A_MK; t1.b_mode = B_NK;
+        t1.M = (int)(mc * N); t1.N = N; t1.K = N;
+        t1.A = m->B0; t1.lda = N; t1.B = m->S; t1.ldb = N; t1.C = m->B1; t1.ldc = N;
+        CES_TRY(gemm(st, t1));
+        GemmCall cz;
+        cz.a_mode = A_MK; cz.b_mode = B_KN;
+        cz.M = N; cz.N = N; cz.K = N;
+        cz.A = m->S; cz.lda = N; cz.B = m->B1; cz.ldb = N; cz.C = m->B2; cz.ldc = N;
+        cz.batch = mc; cz.b_batch_rows = N; cz.c_batch_elems = cells;
+        CES_TRY(gemm(st, cz));
+        // 4. solve; nodal pressure into B0 (cleared: boundary nodes stay zero)
+        CES_CUDA(cudaMemsetAsync(m->B0, 0, (size_t)mc * cells * sizeof(double), st));
+        CES_TRY(pcg_launch(m, m->B2, m->B0, (int)mc, tol, max_iter));
+        // 5. back to the cell centres: T2 = p S2^T, P_z = S2 T2_z
+        GemmCall t2 = t1;
+        t2.A = m->B0; t2.B = m->S2; t2.C = m->B1;
+        CES_TRY(gemm(st, t2));
+        GemmCall pz = cz;
+        pz.A = m->S2; pz.B = m->B1; pz.C = m->B2;
+        CES_TRY(gemm(st, pz));
+        // 6. observations (or the whole field), particle index contiguous
+        const int rows = full_solution ? (int)cells : m->n_obs;
+        dim3 grid((unsigned)ceil_div(mc, 256), (unsigned)rows);
+        darcy_gather_kernel<<<grid, 256, 0, st>>>(m->B2, cells, (int)mc, full_solution ? nullptr : m->obs, rows, G + c0, ldg);
+        CES_LAUNCHED(1);
+    }
+    int iters = 0;
+    CES_CUDA(cudaMemcpyAsync(&iters, m->iters, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CES_CUDA(cudaStreamSynchronize(st));
+    if (iters_host) *iters_host = iters;
+    if (iters >= max_iter) return fail(CES_ERR_STATE, "ces_darcy_forward: CG did not converge in %s%lld iterations", "", max_iter);
+    return CES_OK;
+}
+
+}  // extern "C"

@@ -24,10 +24,16 @@ int gemm_tiles(int M, int N) { return (int)(ceil_div(M, GEMM_BM) * ceil_div(N, G
 int gemm(cudaStream_t st, const GemmCall& c) {
     if (c.M < 1 || c.N < 1 || c.K < 1 || !c.A || !c.B || !c.C) return fail(CES_ERR_INVALID, "gemm: bad shape or null operand%s", "");
     CUtensorMap ma, mb;
-    if (c.a_mode == A_MK) CES_TRY(make_map_2d(&ma, c.A, c.K, c.M, c.lda, 16, 128));
-    else                  CES_TRY(make_map_2d(&ma, c.A, c.M, c.K, c.lda, 16, 16));
-    if (c.b_mode == B_NK) CES_TRY(make_map_2d(&mb, c.B, c.K, c.N, c.ldb, 16, 128));
-    else                  CES_TRY(make_map_2d(&mb, c.B, c.N, c.K, c.ldb, 16, 16));
+    // tensor-map row extents cover every batch of a batched operand
+    const int64_t nb = c.batch > 1 ? c.batch : 1;
+    const int64_t a_rows = (c.a_mode == A_MK ? c.M : c.K) + (nb - 1) * c.a_batch_rows;
+    const int64_t b_rows = (c.b_mode == B_NK ? c.N : c.K) + (nb - 1) * c.b_batch_rows;
+    if (nb > 1 && (c.splits > 1 || c.splitk_ws || c.ssq_partials))
+        return fail(CES_ERR_INVALID, "gemm: batching excludes split-K and sum-of-squares partials%s", "");
+    if (c.a_mode == A_MK) CES_TRY(make_map_2d(&ma, c.A, c.K, a_rows, c.lda, 16, 128));
+    else                  CES_TRY(make_map_2d(&ma, c.A, c.M, a_rows, c.lda, 16, 16));
+    if (c.b_mode == B_NK) CES_TRY(make_map_2d(&mb, c.B, c.K, b_rows, c.ldb, 16, 128));
+    else                  CES_TRY(make_map_2d(&mb, c.B, c.N, b_rows, c.ldb, 16, 16));
 
     GemmArgs a;
     a.M = c.M; a.N = c.N; a.K = c.K;
@@ -41,6 +47,7 @@ int gemm(cudaStream_t st, const GemmCall& c) {
     a.splits = 1;
     a.kblocks_per_split = 0;
     a.splitk_ws = nullptr;
+    a.a_batch_rows = (int)c.a_batch_rows; a.b_batch_rows = (int)c.b_batch_rows; a.c_batch_elems = c.c_batch_elems;
     const int kb_total = (int)ceil_div(c.K, GEMM_BK);
     int splits = c.splits > 1 ? c.splits : 1;
     if (splits > kb_total) splits = kb_total;
@@ -52,7 +59,7 @@ int gemm(cudaStream_t st, const GemmCall& c) {
     a.kblocks_per_split = (int)ceil_div(kb_total, splits);
     a.splits = (int)ceil_div(kb_total, a.kblocks_per_split);
     a.splitk_ws = c.splitk_ws;
-    dim3 grid((unsigned)(a.tiles_m * a.tiles_n), 1, (unsigned)a.splits);
+    dim3 grid((unsigned)(a.tiles_m * a.tiles_n), (unsigned)nb, (unsigned)a.splits);
     int s;
     if (c.a_mode == A_MK && c.b_mode == B_KN) s = launch_one<0, 0>(st, ma, mb, a, grid);
     else if (c.a_mode == A_KM && c.b_mode == B_KN) s = launch_one<1, 0>(st, ma, mb, a, grid);

@@ -46,6 +46,10 @@ struct GemmArgs {
     int tiles_m, tiles_n, group_m;
     int kblocks_per_split, splits;
     int flags;
+    // batching over blockIdx.y: batch z uses operand rows shifted by z*{a,b}_batch_rows (0 = shared operand)
+    // and writes C + z*c_batch_elems.  A batched operand must fill whole TMA boxes along its row axis.
+    int a_batch_rows, b_batch_rows;
+    long long c_batch_elems;
 };
 
 // Byte offset of element (row r, contraction index kk) in a contraction-contiguous 128x16 tile.
@@ -135,17 +139,18 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 const uint32_t a_dst = smem_base + s * GEMM_STAGE_BYTES;
                 const uint32_t b_dst = a_dst + GEMM_TILE_BYTES;
                 const int k0 = (kb_begin + it) * GEMM_BK;
+                const int az = (int)blockIdx.y * args.a_batch_rows, bz = (int)blockIdx.y * args.b_batch_rows;
                 if (A_MODE == 0) {
-                    tma_load_2d(a_dst, &mapA, fb, k0, m0);
+                    tma_load_2d(a_dst, &mapA, fb, k0, m0 + az);
                 } else {
 #pragma unroll
-                    for (int o = 0; o < 8; ++o) tma_load_2d(a_dst + o * 2048, &mapA, fb, m0 + 16 * o, k0);
+                    for (int o = 0; o < 8; ++o) tma_load_2d(a_dst + o * 2048, &mapA, fb, m0 + 16 * o, k0 + az);
                 }
                 if (B_MODE == 1) {
-                    tma_load_2d(b_dst, &mapB, fb, k0, n0);
+                    tma_load_2d(b_dst, &mapB, fb, k0, n0 + bz);
                 } else {
 #pragma unroll
-                    for (int o = 0; o < 8; ++o) tma_load_2d(b_dst + o * 2048, &mapB, fb, n0 + 16 * o, k0);
+                    for (int o = 0; o < 8; ++o) tma_load_2d(b_dst + o * 2048, &mapB, fb, n0 + 16 * o, k0 + bz);
                 }
             }
         }
@@ -213,7 +218,8 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const int m_base = tm * GEMM_BM + wm * 64, n_base = tn * GEMM_BN + wn * 32;
     double ssq = 0.0;
     const bool to_ws = args.splitk_ws != nullptr;
-    double* out = to_ws ? args.splitk_ws + (size_t)blockIdx.z * (size_t)args.M * (size_t)args.N : args.C;
+    double* out = to_ws ? args.splitk_ws + (size_t)blockIdx.z * (size_t)args.M * (size_t)args.N
+                        : args.C + (size_t)blockIdx.y * (size_t)args.c_batch_elems;
     const long long ldo = to_ws ? (long long)args.N : args.ldc;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {

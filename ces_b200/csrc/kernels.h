@@ -31,6 +31,8 @@ struct GemmCall {
     int splits = 1;
     double* splitk_ws = nullptr;      // >= splits*M*N doubles; enables the reduce epilogue
     double diag_add = 0.0;            // reduce epilogue only
+    // batched form: `batch` problems, operand rows shifted by z*{a,b}_batch_rows (0 = shared), C by z*c_batch_elems
+    int64_t batch = 1, a_batch_rows = 0, b_batch_rows = 0, c_batch_elems = 0;
 };
 
 int gemm(cudaStream_t st, const GemmCall& c);

@@ -131,6 +131,19 @@ int64_t ces_launch_count(ces_handle_t h);
 int ces_profile_enable(ces_handle_t h, int on);
 int ces_profile_read(ces_handle_t h, double* gemm_d_ms, int64_t* launches, double* flops);
 
+/* ---- batched 2-D Darcy forward model (ces/darcy.py:9-138 + utilities/mfiles/gaussrnd_coarse.m, solve_gwf.m) ------
+ * ces_darcy_create: N x N mesh (16 <= N <= 128, N % 16 == 0), p active KL modes; HOST operators assembled by the
+ * caller (ces_b200/darcy.py): PhiT (p x N^2, scaled 2-D inverse-DCT basis of the active modes), S (N x N, not-a-knot
+ * spline cell centres -> nodes), S2 (N x N, nodes -> centres); obs_index (n_obs flat cell indices, row-major) or NULL.
+ * ces_darcy_forward: U_dev (p x cols, ld = ldu) -> G_dev (n_obs x cols, or N^2 x cols when full_solution != 0), one
+ * thread-block cluster per member running Jacobi-preconditioned CG to relative residual `tol` (<= 0: 1e-13) with at
+ * most max_iter iterations (<= 0: 40 N); *iters_host receives the largest iteration count of the batch. */
+int ces_darcy_create(int64_t N, int64_t p, const double* PhiT_host, const double* S_host, const double* S2_host,
+                     const int64_t* obs_index_host, int64_t n_obs, void* stream, void** out);
+int ces_darcy_destroy(void* model);
+int ces_darcy_forward(void* model, const double* U_dev, int64_t ldu, int64_t cols, double* G_dev, int64_t ldg,
+                      int full_solution, double tol, int max_iter, int* iters_host);
+
 /* ---- building blocks exported for tests and for callers that own their orchestration ---------------
  * C[M,N] = alpha * op(A) op(B) + beta * C on the FP64 tensor cores.  a_mode: 0 = A is M x K row-major,
  * 1 = A is stored K x M (i.e. A^T given); b_mode: 0 = B is K x N row-major, 1 = B stored N x K.

@@ -1,0 +1,96 @@
+"""Batched Darcy forward model on the B200 against the scipy restatement of ces/darcy.py + the two .m files
+(oracle/darcy_oracle.py; parity with the MATLAB original is unpinned)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from ces_b200 import calibrate, darcy as cdarcy  # noqa: E402
+from oracle import darcy_oracle as do, eks_oracle as eo  # noqa: E402
+
+TOL = 1e-9      # iterative solve (relative residual 1e-13) vs sparse direct
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / np.abs(b).max())
+
+
+@pytest.mark.parametrize("N,p,members,scale", [(16, 10, 7, 1.0), (16, 10, 5, 10.0), (32, 24, 4, 3.0), (64, 64, 4, 1.0),
+                                               (64, 64, 3, 10.0), (128, 256, 2, 1.0)])
+def test_truncated_model_matches_oracle(N, p, members, scale):
+    rng = np.random.default_rng(N + p)
+    U = scale * rng.standard_normal((p, members))
+    m = cdarcy.model_trunc(Nmesh=N, p=p)
+    ref = do.ModelTrunc(Nmesh=N, p=p)
+    assert np.array_equal(m.rank, ref.rank)
+    full = m.solve_ensemble(U, full_solution=True)
+    want = np.stack([ref(U[:, j], full_solution=True) for j in range(members)], axis=1)
+    assert full.shape == (N * N, members)
+    assert _rel(full, want) < TOL
+    obs = rng.choice(N * N, size=50, replace=False)
+    m.obs_index = obs
+    ref.obs_index = obs
+    got = m.solve_ensemble(U, full_solution=False)
+    assert _rel(got, want[obs]) < TOL
+    one = m(U[:, 1])                     # single-particle call of the reference API
+    assert _rel(one, want[obs, 1]) < TOL
+    assert 0 < m.last_iterations < 40 * N
+
+
+def test_full_model_all_coefficients():
+    N = 16
+    m = cdarcy.model(Nmesh=N)
+    ref = do.ModelTrunc(Nmesh=N, p=None)
+    m.set_initial(seed=1)
+    ref.set_initial(seed=1)
+    assert np.array_equal(m.ustar, ref.ustar)
+    got = m(m.ustar, full_solution=True)
+    assert _rel(got, ref(ref.ustar, full_solution=True)) < TOL
+
+
+def test_odd_ensemble_width_and_engine_forward():
+    """enka.G_ens with a device Darcy model; an odd number of particles exercises the re-pack of U^T."""
+    N, p, J = 16, 10, 33
+    rng = np.random.default_rng(0)
+    U = rng.standard_normal((p, J))
+    m = cdarcy.model_trunc(Nmesh=N, p=p)
+    m.obs_index = rng.choice(N * N, size=12, replace=False)
+    ref = do.ModelTrunc(Nmesh=N, p=p)
+    ref.obs_index = m.obs_index
+    e = calibrate.enka(p, 12, J)
+    G = e.G_ens(U, m)
+    want = np.stack([ref(U[:, j]) for j in range(J)], axis=1)
+    assert _rel(G, want) < TOL
+
+
+def test_eks_run_on_darcy_matches_oracle_loop():
+    """sampling.run with the Darcy model resident on the device (the examples/scripts/darcy-flow.py scenario at
+    test size) against the oracle update + the scipy Darcy restatement stepped on the same random stream."""
+    N, p, J, n_obs, T = 16, 10, 24, 12, 3
+    m = cdarcy.model_trunc(Nmesh=N, p=p)
+    m.set_initial(seed=1)
+    ref = do.ModelTrunc(Nmesh=N, p=p)
+    np.random.seed(1)
+    obs = np.random.choice(N * N, n_obs, replace=False)
+    m.obs_index = obs
+    ref.obs_index = obs
+    m.n_obs = n_obs
+    gamma = 0.005
+    Gamma = gamma ** 2 * np.identity(n_obs)
+    y = ref(m.ustar) + gamma * np.random.normal(0, 1, n_obs)
+    s = calibrate.sampling(p=p, n_obs=n_obs, J=J)
+    s.ustar, s.T = m.ustar.reshape(p, -1), T
+    s.mu, s.sigma = np.zeros((p, 1)), 100.0 * np.identity(p)
+    np.random.seed(3)
+    U0 = np.random.normal(0, 1, [p, J])
+    s.run(y, U0, m, Gamma, np.linalg.cholesky(Gamma), t_tol=1e9)
+    np.random.seed(3)
+    U = np.random.normal(0, 1, [p, J])
+    t = None
+    for _ in range(T):
+        G = np.stack([ref(U[:, j]) for j in range(J)], axis=1)
+        o = eo.step("aldi", y, U, G, Gamma, s.mu, s.sigma, s.ustar, np.random.normal(0, 1, [p, J]), t_last=t)
+        U, t = o["Uk"], o["t"]
+    assert _rel(s.Ustar, U) < 1e-6          # three chained steps through an iterative PDE solve
+    assert abs(s.metrics["t"][-1] - t) < 1e-7 * t
+    assert s.Gall.shape == (T + 1, n_obs, J)
