@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libces_b200.so")
 CES_OK = 0
 CES_ERR_INVALID, CES_ERR_STATE, CES_ERR_ALIGN, CES_ERR_NOT_SPD, CES_ERR_CUDA, CES_ERR_NOMEM = -1, -2, -3, -4, -5, -6
 RULES = {"eks": 0, "aldi": 1, "aldi_constant": 2, "eki": 3}
-TS_FROBENIUS, TS_FIXED = 0, 1
+TS_FROBENIUS, TS_FIXED, TS_KEEP = 0, 1, 2
 MAPS = {"lineal": 0, "lineal_log": 1, "elliptic": 2, "banana": 3}
 
 # every symbol include/ces_b200.h declares (tests/test_abi.py checks the .so exports them all)
@@ -23,6 +23,7 @@ EXPORTS = (
     "ces_phase2_centre", "ces_phase3_interact", "ces_phase4a_drift", "ces_phase4_update", "ces_step",
     "ces_step_host", "ces_forward_map", "ces_buffer", "ces_launch_count", "ces_gemm", "ces_potrf", "ces_posv",
     "ces_profile_enable", "ces_profile_read", "ces_darcy_create", "ces_darcy_destroy", "ces_darcy_forward",
+    "ces_peek_step_size", "ces_phase3b_cpp", "ces_phase3c_resolve",
 )
 
 _i64, _int, _dbl, _vp = ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_void_p
@@ -56,7 +57,10 @@ def load():
     lib.ces_set_problem.argtypes = [_vp, _dp, _dp, _dp, _dp, _dp]
     lib.ces_phase1_sums.argtypes = [_vp, _dp, _i64, _dp, _i64]
     lib.ces_phase2_centre.argtypes = [_vp, _int, _dp, _i64, _dp, _i64]
-    lib.ces_phase3_interact.argtypes = [_vp, _int]
+    lib.ces_phase3_interact.argtypes = [_vp, _int, _int]
+    lib.ces_peek_step_size.argtypes = [_vp, _int, _dbl, ctypes.POINTER(_dbl)]
+    lib.ces_phase3b_cpp.argtypes = [_vp]
+    lib.ces_phase3c_resolve.argtypes = [_vp, _int]
     lib.ces_phase4a_drift.argtypes = [_vp, _dbl]
     lib.ces_phase4_update.argtypes = [_vp, _int, _int, _dbl, _dp, _i64, _dp, _i64, _dp, _i64,
                                       ctypes.POINTER(_dbl), ctypes.POINTER(_dbl)]

@@ -251,20 +251,30 @@ class sampling(enka):
             self.radspec = []
             self.metrics = dict((key, []) for key in _METRIC_KEYS)
 
-    def _step_options(self, kwargs):
+    def _step_options(self, rule, kwargs):
+        """(fixed_h, resolve) for Engine.step from the reference's ``time_step`` kwargs
+        (ces/calibrate.py:247-260 for hk; :439-441 / :470-473 for the hk C^pp + Gamma re-solve of D)."""
         kind = kwargs.get('time_step', None)
-        if kind is None:
-            return None
-        if kind in ('constant', 'mix', 'spectral', 'adaptive'):
+        if kind is None or rule == 'aldi_constant':          # aldi_constant sets its own hk (:519)
+            return None, None
+        const = kwargs.get('delta_t', 1. / (self.T / 2))
+        if kind == 'constant':
+            return const, ('always' if rule in ('eks', 'aldi') else None)
+        if kind == 'mix':
+            t = self.metrics['t'] if hasattr(self, 'metrics') else []
+            spun_up = not (len(t) == 0 or t[-1] < kwargs.get('spinup', 4.))
+            resolve = ((t[-1] if len(t) else 0.0), 1.0) if rule == 'aldi' else None     # eks never re-solves for 'mix'
+            return (const if spun_up else None), resolve
+        if kind in ('spectral', 'adaptive'):
             raise NotImplementedError(
-                "time_step=%r needs the Gamma -> hk*C^pp + Gamma re-solve (ces/calibrate.py:439-441, 470-473), "
-                "scheduled after the default path (SURVEY.md section 8f rank 3)" % (kind,))
+                "time_step=%r: 'spectral' needs a non-symmetric J x J eigen-solve outside the accelerated path and "
+                "'adaptive' calls a method the reference does not define (ces/calibrate.py:250, 255)" % (kind,))
         raise ValueError("unknown time_step %r" % (kind,))
 
     # ------------------------------------------------------------------ single updates on numpy arrays
     def _update_host(self, rule, y_obs, U0, Geval, Gamma, kwargs):
         self._ensure_metrics()
-        fixed = self._step_options(kwargs)
+        fixed, resolve = self._step_options(rule, kwargs)
         U0 = np.asarray(U0, dtype=np.float64)
         eng = self._get_engine(U0.shape[1])
         self._sync_problem(eng, y_obs, Gamma)
@@ -272,7 +282,7 @@ class sampling(enka):
         if rule != 'eki':
             xi = self._draw_noise(U0.shape, kwargs)
         Uk, hk, met = eng.step_host(rule, U0, np.asarray(Geval, dtype=np.float64)[:self.n_obs], xi, fixed_h=fixed,
-                                    switch=kwargs.get('switch', 1.))
+                                    switch=kwargs.get('switch', 1.), resolve=resolve)
         self._record(met, hk)
         return Uk
 
@@ -325,7 +335,8 @@ class sampling(enka):
                                       "accelerated path this round (SURVEY.md section 8f rank 2)")
         if mtype != 'map':
             raise ValueError("model.type must be 'map' or 'pde'")
-        fixed = self._step_options(kwargs)
+        self._ensure_metrics()
+        self._step_options(rule, kwargs)            # validates time_step before any work
         group = getattr(self, 'group', None)
 
         U0 = np.ascontiguousarray(U0, dtype=np.float64)
@@ -376,7 +387,9 @@ class sampling(enka):
                 if rule != 'eki':
                     xi = self._draw_noise((self.p, J), kwargs)          # same stream on every rank
                     xi_dev = torch.from_numpy(np.ascontiguousarray(xi[:, lo:hi])).to(dev)
-                U_dev, hk, met = eng.step(rule, U_dev, G_cur, xi_dev, fixed_h=fixed, switch=kwargs.get('switch', 1.))
+                fixed, resolve = self._step_options(rule, kwargs)     # 'mix' depends on the time reached so far
+                U_dev, hk, met = eng.step(rule, U_dev, G_cur, xi_dev, fixed_h=fixed, switch=kwargs.get('switch', 1.),
+                                          resolve=resolve)
                 self._record(met, hk)
             # an unknown ``update`` leaves the ensemble unchanged and records nothing, like :364-369 --
             # the reference then fails on the empty ``metrics['t']``; so do we

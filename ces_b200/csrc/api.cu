@@ -27,10 +27,18 @@ struct ces_handle_s {
     int64_t ssq_cap = 0, splitk_cap = 0;
     int syrk_splits = 1;
     int* info = nullptr;
+    // K11 (time_step 'constant' / 'mix'): D re-solved with Gamma -> h*C^pp + Gamma
+    std::vector<double> gamma_host;
+    double *GammaD = nullptr, *Cpp = nullptr, *Mk = nullptr, *MkLinv = nullptr, *MkInv = nullptr, *Wr = nullptr, *cpp_ws = nullptr;
+    int cpp_splits = 1;
     // host staging
     double* hS = nullptr;   // pinned, S_COUNT doubles + 1 int
     int* hinfo = nullptr;
     double *stage_U = nullptr, *stage_G = nullptr, *stage_xi = nullptr, *stage_out = nullptr;
+    double* pending_out = nullptr;      // host destination of stage_out, copied inside phase 4 before its final sync
+    int64_t pending_rows = 0;
+    cudaStream_t copy_st = nullptr;     // uploads xi while phases 1-3 run
+    cudaEvent_t copy_ev = nullptr, start_ev = nullptr;
     std::vector<void*> allocs;
     // optional event timing of the D = E^T W launches
     bool profile = false;
@@ -192,6 +200,9 @@ int ces_destroy(ces_handle_t h) {
     cudaStreamSynchronize(h->st);
     for (void* ptr : h->allocs) cudaFree(ptr);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    if (h->copy_ev) cudaEventDestroy(h->copy_ev);
+    if (h->start_ev) cudaEventDestroy(h->start_ev);
+    if (h->copy_st) cudaStreamDestroy(h->copy_st);
     if (h->hS) cudaFreeHost(h->hS);
     delete h;
     cudaGetLastError();
@@ -209,6 +220,8 @@ int ces_set_problem(ces_handle_t h, const double* y, const double* Gamma, const 
     CES_CUDA(cudaMemcpyAsync(h->ustar, ustar, p * sizeof(double), cudaMemcpyHostToDevice, h->st));
     CES_CUDA(cudaStreamSynchronize(h->st));
 
+    h->gamma_host.assign(Gamma, Gamma + k * k);
+    if (h->GammaD) CES_TRY(upload_square(h, Gamma, k, h->GammaD, h->ldk));
     h->gamma_diag = is_diagonal(Gamma, k);
     if (h->gamma_diag) {
         std::vector<double> inv(k);
@@ -314,18 +327,10 @@ int ces_phase2_centre(ces_handle_t h, int rule, const double* U, int64_t ldu, co
     return CES_OK;
 }
 
-int ces_phase3_interact(ces_handle_t h, int rule) {
-    CES_TRY(valid(h, true));
-    if (rule != h->last_rule) return fail(CES_ERR_STATE, "phase3: rule differs from phase2%s", "");
+// D = (1/J) E^T Wsrc by source block s (rows of D) and column panel (K3, K4); V = U~ D (K5).
+static int interaction_loops(ces_handle_t h, const double* Wsrc, bool accumulate_ssq) {
     const int64_t p = h->p, k = h->k, ld = h->ldJ;
     cudaStream_t st = h->st;
-    // chol(C^uu)  (K7); EKI has no noise term and skips it
-    if (rule != CES_RULE_EKI) {
-        CES_CUDA(cudaMemcpy2DAsync(h->L, h->ldp * sizeof(double), h->Cuu, h->ldp * sizeof(double), p * sizeof(double), p,
-                                   cudaMemcpyDeviceToDevice, st));
-        CES_TRY(potrf_lower(st, h->L, h->ldp, p, h->Linv, kLinvLd, h->info));
-    }
-    // D = (1/J) E^T W by source block s (rows of D) and column panel (K3, K4); V = U~ D (K5)
     int64_t npart = 0;
     const double invJ = 1.0 / (double)h->Jg;
     for (int64_t c0 = 0; c0 < h->Jl; c0 += h->panel) {
@@ -335,13 +340,15 @@ int ces_phase3_interact(ces_handle_t h, int rule) {
             g1.a_mode = A_KM; g1.b_mode = B_KN;
             g1.M = (int)h->Jl; g1.N = (int)nc; g1.K = (int)k;
             g1.A = e_block(h, s); g1.lda = ld;
-            g1.B = h->W + c0; g1.ldb = ld;
+            g1.B = Wsrc + c0; g1.ldb = ld;
             g1.C = h->D; g1.ldc = h->ldD;
             g1.alpha = invJ;
-            const int tiles = gemm_tiles(g1.M, g1.N);
-            if (npart + tiles > h->ssq_cap) return fail(CES_ERR_STATE, "phase3: partial-sum buffer too small%s", "");
-            g1.ssq_partials = h->ssq_partials + npart;
-            npart += tiles;
+            if (accumulate_ssq) {
+                const int tiles = gemm_tiles(g1.M, g1.N);
+                if (npart + tiles > h->ssq_cap) return fail(CES_ERR_STATE, "phase3: partial-sum buffer too small%s", "");
+                g1.ssq_partials = h->ssq_partials + npart;
+                npart += tiles;
+            }
             if (h->profile) {
                 while (h->ev_pool.size() < h->ev_used + 2) {
                     cudaEvent_t e;
@@ -366,8 +373,91 @@ int ces_phase3_interact(ces_handle_t h, int rule) {
             CES_TRY(gemm(st, g2));
         }
     }
-    CES_TRY(sum_vector(st, h->ssq_partials, npart, h->S + S_SSQ));
+    if (accumulate_ssq) CES_TRY(sum_vector(st, h->ssq_partials, npart, h->S + S_SSQ));
     return CES_OK;
+}
+
+int ces_phase3_interact(ces_handle_t h, int rule, int skip_interaction) {
+    CES_TRY(valid(h, true));
+    if (rule != h->last_rule) return fail(CES_ERR_STATE, "phase3: rule differs from phase2%s", "");
+    const int64_t p = h->p;
+    cudaStream_t st = h->st;
+    // chol(C^uu)  (K7); EKI has no noise term and skips it
+    if (rule != CES_RULE_EKI) {
+        CES_CUDA(cudaMemcpy2DAsync(h->L, h->ldp * sizeof(double), h->Cuu, h->ldp * sizeof(double), p * sizeof(double), p,
+                                   cudaMemcpyDeviceToDevice, st));
+        CES_TRY(potrf_lower(st, h->L, h->ldp, p, h->Linv, kLinvLd, h->info));
+    }
+    if (skip_interaction) return CES_OK;       // 'constant' step size: D is formed once, by ces_phase3c_resolve
+    return interaction_loops(h, h->W, true);
+}
+
+int ces_peek_step_size(ces_handle_t h, int ts_kind, double fixed_h, double* hk_host) {
+    CES_TRY(valid(h, true));
+    if (ts_kind != CES_TS_FROBENIUS && ts_kind != CES_TS_FIXED) return fail(CES_ERR_INVALID, "unknown step-size rule%s", "");
+    const double alphaJ = (double)(h->p + 1) / (double)h->Jg;
+    CES_TRY(step_scalars(h->st, h->S, ts_kind == CES_TS_FIXED ? 1 : 0, fixed_h, alphaJ));
+    CES_CUDA(cudaMemcpyAsync(h->hS, h->S, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CES_CUDA(cudaStreamSynchronize(h->st));
+    if (hk_host) *hk_host = h->hS[S_H];
+    return CES_OK;
+}
+
+int ces_phase3b_cpp(ces_handle_t h) {
+    CES_TRY(valid(h, true));
+    const int64_t k = h->k, ld = h->ldJ;
+    cudaStream_t st = h->st;
+    if (!h->Cpp) {
+        const int64_t tm = ceil_div(k, GEMM_BM), lower = tm * (tm + 1) / 2;
+        int64_t sp = ceil_div(296, lower);
+        const int64_t kb = ceil_div(ld, GEMM_BK);
+        if (sp > kb) sp = kb;
+        if (sp > 64) sp = 64;
+        if (sp < 1) sp = 1;
+        h->cpp_splits = (int)sp;
+        CES_TRY(dalloc(h, &h->Cpp, k * h->ldk));
+        CES_TRY(dalloc(h, &h->cpp_ws, sp * k * k));
+        CES_TRY(dalloc(h, &h->Mk, k * h->ldk));
+        CES_TRY(dalloc(h, &h->MkInv, k * h->ldk));
+        CES_TRY(dalloc(h, &h->MkLinv, round_up(k, CHOL_NB) * kLinvLd));
+        CES_TRY(dalloc(h, &h->Wr, k * ld));
+        CES_TRY(dalloc(h, &h->GammaD, k * h->ldk));
+        if (!h->R) CES_TRY(dalloc(h, &h->R, k * ld));
+        CES_TRY(upload_square(h, h->gamma_host.data(), k, h->GammaD, h->ldk));
+    }
+    // C^pp = cov(G, bias=True) = E E^T / J   (ces/calibrate.py:440, 472): local part, lower tiles, mirrored
+    GemmCall g;
+    g.a_mode = A_MK; g.b_mode = B_NK;
+    g.M = (int)k; g.N = (int)k; g.K = (int)h->Jl;
+    g.A = e_block(h, h->rank); g.lda = ld; g.B = g.A; g.ldb = ld; g.C = h->Cpp; g.ldc = h->ldk;
+    g.alpha = 1.0 / (double)h->Jg;
+    g.flags = GEMM_C_LOWER_ONLY;
+    g.splits = h->cpp_splits; g.splitk_ws = h->cpp_ws;
+    return gemm(st, g);
+}
+
+int ces_phase3c_resolve(ces_handle_t h, int rule) {
+    CES_TRY(valid(h, true));
+    if (rule != h->last_rule) return fail(CES_ERR_STATE, "phase3c: rule differs from phase2%s", "");
+    if (!h->Cpp) return fail(CES_ERR_STATE, "phase3c: ces_phase3b_cpp has not run%s", "");
+    const int64_t k = h->k, ld = h->ldJ;
+    cudaStream_t st = h->st;
+    // R = G - y: stored by phase 2 for dense Gamma, rebuilt as E + (mean - y) 1^T for diagonal Gamma
+    if (h->gamma_diag) {
+        CES_CUDA(cudaMemcpyAsync(h->R, e_block(h, h->rank), (size_t)k * ld * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        CES_TRY(add_col_vector(st, h->R, ld, k, h->cols, h->cvec, 1.0, nullptr));
+    }
+    // M = hk * C^pp + Gamma with the hk of ces_peek_step_size (device scalar), inverted through its Cholesky factor
+    CES_TRY(form_implicit(st, h->Cpp, h->ldk, h->GammaD, h->ldk, nullptr, h->S + S_H, k, h->Mk, h->ldk));
+    CES_TRY(potrf_lower(st, h->Mk, h->ldk, k, h->MkLinv, kLinvLd, h->info));
+    CES_TRY(spd_inverse_from_factor(st, h->Mk, h->ldk, k, h->MkLinv, kLinvLd, h->MkInv, h->ldk));
+    GemmCall g;
+    g.a_mode = A_MK; g.b_mode = B_KN;
+    g.M = (int)k; g.N = (int)h->Jl; g.K = (int)k;
+    g.A = h->MkInv; g.lda = h->ldk; g.B = h->R; g.ldb = ld; g.C = h->Wr; g.ldc = ld;
+    CES_TRY(gemm(st, g));
+    // the step size stays the one computed from the Gamma-only D (ces/calibrate.py:437 precedes :439-441)
+    return interaction_loops(h, h->Wr, false);
 }
 
 int ces_phase4a_drift(ces_handle_t h, double switch_) {
@@ -394,7 +484,8 @@ int ces_phase4_update(ces_handle_t h, int rule, int ts_kind, double fixed_h, con
     CES_TRY(valid(h, true));
     if (rule != h->last_rule) return fail(CES_ERR_STATE, "phase4: rule differs from phase2%s", "");
     if (!U || !Uout || (rule != CES_RULE_EKI && !xi)) return fail(CES_ERR_INVALID, "phase4: null pointer%s", "");
-    if (ts_kind != CES_TS_FROBENIUS && ts_kind != CES_TS_FIXED) return fail(CES_ERR_INVALID, "unknown step-size rule%s", "");
+    if (ts_kind != CES_TS_FROBENIUS && ts_kind != CES_TS_FIXED && ts_kind != CES_TS_KEEP)
+        return fail(CES_ERR_INVALID, "unknown step-size rule%s", "");
     const int64_t p = h->p, ld = h->ldJ;
     cudaStream_t st = h->st;
     const double alphaJ = (double)(p + 1) / (double)h->Jg;
@@ -411,7 +502,7 @@ int ces_phase4_update(ces_handle_t h, int rule, int ts_kind, double fixed_h, con
     }
 
     const int kind = (rule == CES_RULE_ALDI_CONSTANT) ? 2 : (ts_kind == CES_TS_FIXED ? 1 : 0);
-    CES_TRY(step_scalars(st, S, kind, fixed_h, alphaJ));
+    if (ts_kind != CES_TS_KEEP || rule == CES_RULE_ALDI_CONSTANT) CES_TRY(step_scalars(st, S, kind, fixed_h, alphaJ));
 
     GemmCall noise;   // += sqrt(2h) chol(C) xi     (K8; L lower triangular -> skip the zero blocks)
     noise.a_mode = A_MK; noise.b_mode = B_KN;
@@ -463,6 +554,11 @@ int ces_phase4_update(ces_handle_t h, int rule, int ts_kind, double fixed_h, con
         }
     }
     CES_CUDA(cudaMemcpyAsync(h->hS, S, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (h->pending_out) {               // ces_step_host: result copy rides on the same final synchronisation
+        const size_t wbytes = h->Jl * sizeof(double);
+        if (ldo == h->Jl) CES_CUDA(cudaMemcpyAsync(h->pending_out, Uout, (size_t)h->pending_rows * wbytes, cudaMemcpyDeviceToHost, st));
+        else CES_CUDA(cudaMemcpy2DAsync(h->pending_out, wbytes, Uout, ldo * sizeof(double), wbytes, h->pending_rows, cudaMemcpyDeviceToHost, st));
+    }
     CES_TRY(check_info(h, "cov(U)"));   // synchronises the stream
     if (hk_host) *hk_host = h->hS[S_H];
     if (metrics_host) {
@@ -482,7 +578,7 @@ int ces_step(ces_handle_t h, int rule, int ts_kind, double fixed_h, double switc
     if (h->nranks != 1) return fail(CES_ERR_STATE, "ces_step is single-GPU; use the phases with nranks > 1%s", "");
     CES_TRY(ces_phase1_sums(h, U, ldu, G, ldg));
     CES_TRY(ces_phase2_centre(h, rule, U, ldu, G, ldg));
-    CES_TRY(ces_phase3_interact(h, rule));
+    CES_TRY(ces_phase3_interact(h, rule, 0));
     if (rule == CES_RULE_ALDI_CONSTANT) CES_TRY(ces_phase4a_drift(h, switch_));
     return ces_phase4_update(h, rule, ts_kind, fixed_h, U, ldu, xi, ldxi, Uout, ldo, hk_host, metrics_host);
 }
@@ -499,14 +595,38 @@ int ces_step_host(ces_handle_t h, int rule, int ts_kind, double fixed_h, double 
         CES_TRY(dalloc(h, &h->stage_xi, p * ld));
         CES_TRY(dalloc(h, &h->stage_out, p * ld));
     }
+    if (!h->copy_st) {
+        CES_CUDA(cudaStreamCreateWithFlags(&h->copy_st, cudaStreamNonBlocking));
+        CES_CUDA(cudaEventCreateWithFlags(&h->copy_ev, cudaEventDisableTiming));
+        CES_CUDA(cudaEventCreateWithFlags(&h->start_ev, cudaEventDisableTiming));
+    }
     const size_t wb = J * sizeof(double), pb = ld * sizeof(double);
-    CES_CUDA(cudaMemcpy2DAsync(h->stage_U, pb, U, wb, wb, p, cudaMemcpyHostToDevice, h->st));
-    CES_CUDA(cudaMemcpy2DAsync(h->stage_G, pb, G, wb, wb, k, cudaMemcpyHostToDevice, h->st));
-    if (xi) CES_CUDA(cudaMemcpy2DAsync(h->stage_xi, pb, xi, wb, wb, p, cudaMemcpyHostToDevice, h->st));
-    CES_TRY(ces_step(h, rule, ts_kind, fixed_h, switch_, h->stage_U, ld, h->stage_G, ld, xi ? h->stage_xi : nullptr, ld,
-                     h->stage_out, ld, hk_host, metrics_host));
-    CES_CUDA(cudaMemcpy2DAsync(Uout, wb, h->stage_out, pb, wb, p, cudaMemcpyDeviceToHost, h->st));
-    CES_CUDA(cudaStreamSynchronize(h->st));
+    auto h2d = [&](double* dst, const double* src, int64_t rows, cudaStream_t s) -> cudaError_t {
+        if (ld == J) return cudaMemcpyAsync(dst, src, (size_t)rows * wb, cudaMemcpyHostToDevice, s);
+        return cudaMemcpy2DAsync(dst, pb, src, wb, wb, rows, cudaMemcpyHostToDevice, s);
+    };
+    // the noise is needed only by phase 4: upload it on a second stream while phases 1-3 compute
+    // (ordered after the previous step's use of the staging buffer through start_ev)
+    if (xi) {
+        CES_CUDA(cudaEventRecord(h->start_ev, h->st));
+        CES_CUDA(cudaStreamWaitEvent(h->copy_st, h->start_ev, 0));
+        CES_CUDA(h2d(h->stage_xi, xi, p, h->copy_st));
+        CES_CUDA(cudaEventRecord(h->copy_ev, h->copy_st));
+    }
+    CES_CUDA(h2d(h->stage_U, U, p, h->st));
+    CES_CUDA(h2d(h->stage_G, G, k, h->st));
+    CES_TRY(ces_phase1_sums(h, h->stage_U, ld, h->stage_G, ld));
+    CES_TRY(ces_phase2_centre(h, rule, h->stage_U, ld, h->stage_G, ld));
+    CES_TRY(ces_phase3_interact(h, rule, 0));
+    if (rule == CES_RULE_ALDI_CONSTANT) CES_TRY(ces_phase4a_drift(h, switch_));
+    if (xi) CES_CUDA(cudaStreamWaitEvent(h->st, h->copy_ev, 0));
+    // phase 4 ends with a stream synchronisation (status + scalars); queue the result copy before it
+    h->pending_out = Uout;
+    h->pending_rows = p;
+    int s4 = ces_phase4_update(h, rule, ts_kind, fixed_h, h->stage_U, ld, xi ? h->stage_xi : nullptr, ld, h->stage_out, ld,
+                               hk_host, metrics_host);
+    h->pending_out = nullptr;
+    CES_TRY(s4);
     return CES_OK;
 }
 
@@ -584,6 +704,7 @@ int ces_buffer(ces_handle_t h, const char* name, double** ptr, int64_t* rows, in
     else if (n == "w") { q = h->W; r = h->k; c = h->ldJ; l = h->ldJ; }
     else if (n == "v") { q = h->V; r = h->p; c = h->ldJ; l = h->ldJ; }
     else if (n == "z") { q = h->Z; r = h->p; c = h->ldJ; l = h->ldJ; }
+    else if (n == "cpp") { q = h->Cpp; r = h->k; c = h->ldk; l = h->ldk; }
     else if (n == "d_panel") { q = h->D; r = h->ldJ; c = h->ldD; l = h->ldD; }
     else return fail(CES_ERR_INVALID, "ces_buffer: unknown buffer '%s'", name);
     *ptr = q;

@@ -26,37 +26,67 @@ def shard_range(J, rank, nranks):
     return lo, min(J, lo + w)
 
 
-def run_sharded_phases(phases, buffer, dist, group, rank, p, k, rule):
-    """The collectives between the phases of one column-sharded update (include/ces_b200.h):
+def run_phases(phases, buffer, comm, p, k, rule, resolve=None):
+    """One update as phases with the collectives of a column-sharded ensemble in between
+    (include/ces_b200.h).  ``comm`` is None on a single GPU, else ``(dist, group, rank)``:
 
         sums      -> all-reduce(sum)  "sums"  (k + p doubles)            means of G and U
         centre    -> all-reduce(sum)  "cuu"   (p x ldp)                  C^uu from the local U~ U~^T
                      all-gather       "e_all", "ut_all" (rank-major)     every rank needs all of E and U~
         interact  -> all-reduce(sum)  "scalars"[0:5]                     ||D||_F^2 and the four diagnostics
+        [peek -> cpp -> all-reduce(sum) "cpp" (k x ldk) -> resolve]      non-default time_step only (K11)
         drift     -> all-reduce(max)  "scalars"[5:6]                     aldi_constant only
         update
 
-    ``phases`` maps those names to callables, ``buffer(name)`` returns the torch tensor the collective
-    runs on.  The engine passes the ctypes calls; tests/test_multirank_gloo.py passes a numpy stand-in to
-    exercise this orchestration over gloo without a GPU."""
+    ``resolve``: None (default step size rule), "always" ('constant': D is formed once, with
+    hk C^pp + Gamma), or ``(t_last, threshold)`` ('mix': re-solve when t_last + hk > threshold,
+    ces/calibrate.py:470-473).  ``phases`` maps the names to callables, ``buffer(name)`` returns the torch
+    tensor a collective runs on.  The engine passes the ctypes calls; tests/test_multirank_gloo.py passes a
+    numpy stand-in to exercise this orchestration over gloo without a GPU."""
+    if comm is not None:
+        dist, group, rank = comm
+
+        def allreduce(t, op=None):
+            dist.all_reduce(t, group=group) if op is None else dist.all_reduce(t, op=op, group=group)
+
+        def allreduce_slice(t, lo, hi, op=None):
+            part = t[0, lo:hi].clone()
+            allreduce(part, op)
+            t[0, lo:hi] = part
+    else:
+        rank = 0
+
+        def allreduce(t, op=None):
+            return None
+
+        def allreduce_slice(t, lo, hi, op=None):
+            return None
+
     phases["sums"]()
-    dist.all_reduce(buffer("sums"), group=group)
+    allreduce(buffer("sums") if comm is not None else None)
     phases["centre"]()
-    dist.all_reduce(buffer("cuu"), group=group)
-    e_all, ut_all = buffer("e_all"), buffer("ut_all")
-    dist.all_gather_into_tensor(e_all, e_all[rank * k:(rank + 1) * k].clone(), group=group)
-    dist.all_gather_into_tensor(ut_all, ut_all[rank * p:(rank + 1) * p].clone(), group=group)
-    phases["interact"]()
-    scal = buffer("scalars")
-    head = scal[0, 0:5].clone()
-    dist.all_reduce(head, group=group)
-    scal[0, 0:5] = head
+    if comm is not None:
+        allreduce(buffer("cuu"))
+        e_all, ut_all = buffer("e_all"), buffer("ut_all")
+        dist.all_gather_into_tensor(e_all, e_all[rank * k:(rank + 1) * k].clone(), group=group)
+        dist.all_gather_into_tensor(ut_all, ut_all[rank * p:(rank + 1) * p].clone(), group=group)
+    phases["interact"](resolve == "always")
+    if comm is not None:
+        allreduce_slice(buffer("scalars"), 0, 5)
+    keep = False
+    if resolve is not None:
+        hk = phases["peek"]()
+        if resolve == "always" or resolve[0] + hk > resolve[1]:
+            phases["cpp"]()
+            if comm is not None:
+                allreduce(buffer("cpp"))
+            phases["resolve"]()
+        keep = True
     if rule == "aldi_constant":
         phases["drift"]()
-        top = scal[0, 5:6].clone()
-        dist.all_reduce(top, op=dist.ReduceOp.MAX, group=group)
-        scal[0, 5:6] = top
-    phases["update"]()
+        if comm is not None:
+            allreduce_slice(buffer("scalars"), 5, 6, dist.ReduceOp.MAX)
+    phases["update"](keep)
 
 
 class _DeviceView(object):
@@ -160,9 +190,10 @@ class Engine(object):
         return ctypes.c_void_p(t.data_ptr()), int(t.stride(0))
 
     # ------------------------------------------------------------------ one update
-    def step(self, rule, U, G, xi, out=None, fixed_h=None, switch=1.0):
+    def step(self, rule, U, G, xi, out=None, fixed_h=None, switch=1.0, resolve=None):
         """One update on this rank's columns.  U (p, cols), G (k, cols), xi (p, cols) are float64 CUDA
-        tensors; returns (U_next, hk, metrics dict).  ``fixed_h`` selects the 'constant' step size."""
+        tensors; returns (U_next, hk, metrics dict).  ``fixed_h`` gives the step size ('constant', 'mix' after
+        spin-up); ``resolve`` asks for the hk C^pp + Gamma re-solve of D (see ``run_phases``)."""
         torch = self.torch
         r = _lib.RULES[rule]
         ts = _lib.TS_FIXED if fixed_h is not None else _lib.TS_FROBENIUS
@@ -177,34 +208,52 @@ class Engine(object):
         else:
             Xp, ldx = ctypes.c_void_p(0), 0
         lib, h = self.lib, self.h
-        if self.nranks == 1:
+        if self.nranks == 1 and resolve is None:
             _lib.check(lib.ces_step(h, r, ts, fh, float(switch), Up, ldu, Gp, ldg, Xp, ldx, Op, ldo,
                                     ctypes.byref(self._hk), self._met))
         else:
+            def peek():
+                hk = ctypes.c_double()
+                _lib.check(lib.ces_peek_step_size(h, ts, fh, ctypes.byref(hk)))
+                return hk.value
+
             phases = {
                 "sums": lambda: _lib.check(lib.ces_phase1_sums(h, Up, ldu, Gp, ldg)),
                 "centre": lambda: _lib.check(lib.ces_phase2_centre(h, r, Up, ldu, Gp, ldg)),
-                "interact": lambda: _lib.check(lib.ces_phase3_interact(h, r)),
+                "interact": lambda skip: _lib.check(lib.ces_phase3_interact(h, r, 1 if skip else 0)),
+                "peek": peek,
+                "cpp": lambda: _lib.check(lib.ces_phase3b_cpp(h)),
+                "resolve": lambda: _lib.check(lib.ces_phase3c_resolve(h, r)),
                 "drift": lambda: _lib.check(lib.ces_phase4a_drift(h, float(switch))),
-                "update": lambda: _lib.check(lib.ces_phase4_update(h, r, ts, fh, Up, ldu, Xp, ldx, Op, ldo,
-                                                                   ctypes.byref(self._hk), self._met)),
+                "update": lambda keep: _lib.check(lib.ces_phase4_update(
+                    h, r, _lib.TS_KEEP if keep else ts, fh, Up, ldu, Xp, ldx, Op, ldo, ctypes.byref(self._hk), self._met)),
             }
-            run_sharded_phases(phases, self.buffer, self.dist, self.group, self.rank, self.p, self.k, rule)
+            comm = (self.dist, self.group, self.rank) if self.nranks > 1 else None
+            run_phases(phases, self.buffer, comm, self.p, self.k, rule, resolve)
         met = {key: float(self._met[i]) for i, key in enumerate(_METRIC_KEYS)}
         return out, float(self._hk.value), met
 
-    def step_host(self, rule, U, G, xi, fixed_h=None, switch=1.0):
+    def step_host(self, rule, U, G, xi, fixed_h=None, switch=1.0, resolve=None):
         """The same update on host numpy arrays (single GPU): the copies to and from the device are part
         of the call.  This is what ``sampling.eks_update*`` invoke."""
         if self.nranks != 1:
             raise RuntimeError("step_host is single-GPU; shard device tensors and call step()")
+        if resolve is not None:
+            # non-default time_step: the phase-by-phase device path, with explicit copies around it
+            torch = self.torch
+            dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+            out, hk, met = self.step(rule, dev(U), dev(G), dev(xi) if xi is not None else None, fixed_h=fixed_h,
+                                     switch=switch, resolve=resolve)
+            return out.cpu().numpy(), hk, met
         r = _lib.RULES[rule]
         ts = _lib.TS_FIXED if fixed_h is not None else _lib.TS_FROBENIUS
         fh = float(fixed_h) if fixed_h is not None else 0.0
         U = np.ascontiguousarray(U, dtype=np.float64)
         G = np.ascontiguousarray(G, dtype=np.float64)
         assert U.shape == (self.p, self.J) and G.shape == (self.k, self.J), (U.shape, G.shape)
-        out = np.empty_like(U)
+        # a fresh array per call like the reference (callers keep references in Uall), in page-locked memory
+        # from torch's caching host allocator so the device->host copy runs at full PCIe rate
+        out = self.torch.empty((self.p, self.J), dtype=self.torch.float64, pin_memory=True).numpy()
         if xi is not None:
             xi = np.ascontiguousarray(xi, dtype=np.float64)
             assert xi.shape == U.shape

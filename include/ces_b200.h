@@ -48,6 +48,7 @@ extern "C" {
 /* step-size rules (ces/calibrate.py:247-260) */
 #define CES_TS_FROBENIUS 0        /* h = 1 / (||D||_F + 1e-8), :248                                  */
 #define CES_TS_FIXED 1            /* h given by the caller ('constant', and 'mix' after spin-up)     */
+#define CES_TS_KEEP 2             /* phase 4 keeps the h fixed earlier by ces_peek_step_size          */
 
 /* forward maps (ces/utils.py) */
 #define CES_MAP_LINEAL 0          /* A theta + b           :25-31  */
@@ -93,7 +94,15 @@ int ces_set_problem(ces_handle_t h, const double* y_host, const double* Gamma_ho
  * U, G, xi, U_out are device pointers to this rank's columns with leading dimensions ld*.  */
 int ces_phase1_sums(ces_handle_t h, const double* U_dev, int64_t ldu, const double* G_dev, int64_t ldg);
 int ces_phase2_centre(ces_handle_t h, int rule, const double* U_dev, int64_t ldu, const double* G_dev, int64_t ldg);
-int ces_phase3_interact(ces_handle_t h, int rule);
+int ces_phase3_interact(ces_handle_t h, int rule, int skip_interaction);
+/* Non-default time_step modes ('constant', 'mix'; ces/calibrate.py:439-441, 470-473): after phase 3 (and its
+ * all-reduce) ces_peek_step_size fixes and returns the step size hk this step uses; ces_phase3b_cpp forms the local
+ * part of C^pp = cov(G, bias=True) = E E^T / J  [host: all-reduce(sum) of ces_buffer("cpp")]; ces_phase3c_resolve
+ * recomputes D = (1/J) E^T (hk C^pp + Gamma)^-1 R and V = U~ D.  Phase 4 is then called with CES_TS_KEEP.  With a
+ * caller-given hk ('constant') phase 3 may skip forming the Gamma-only D (skip_interaction = 1). */
+int ces_peek_step_size(ces_handle_t h, int ts_kind, double fixed_h, double* hk_host);
+int ces_phase3b_cpp(ces_handle_t h);
+int ces_phase3c_resolve(ces_handle_t h, int rule);
 int ces_phase4a_drift(ces_handle_t h, double switch_);
 int ces_phase4_update(ces_handle_t h, int rule, int ts_kind, double fixed_h, const double* U_dev, int64_t ldu,
                       const double* xi_dev, int64_t ldxi, double* Uout_dev, int64_t ldo, double* hk_host,
@@ -118,7 +127,7 @@ int ces_forward_map(ces_handle_t h, int map_kind, const double* A_dev, int64_t l
 
 /* Named device buffers of the handle, for the host-side collectives and for tests:
  * "sums" (k+p), "cuu" (p x ldp), "e_all" (nranks x k x ldJ), "ut_all" (nranks x p x ldJ), "scalars" (16),
- * "w" (k x ldJ), "v" (p x ldJ), "chol" (p x ldp), "d_panel".  rows/cols/ld may be NULL. */
+ * "w" (k x ldJ), "v" (p x ldJ), "chol" (p x ldp), "cpp" (k x ldk, after ces_phase3b_cpp), "d_panel".  rows/cols/ld may be NULL. */
 int ces_buffer(ces_handle_t h, const char* name, double** ptr_dev, int64_t* rows, int64_t* cols, int64_t* ld);
 
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */

@@ -30,10 +30,11 @@ class NumpyPhases(object):
     def buffer(self, name):
         return self.buf[name]
 
-    def bind(self, rule, U, G, xi, switch=1.0):
-        self.rule, self.U, self.G, self.xi, self.switch = rule, U, G, xi, switch
+    def bind(self, rule, U, G, xi, switch=1.0, fixed_h=None):
+        self.rule, self.U, self.G, self.xi, self.switch, self.fixed_h = rule, U, G, xi, switch, fixed_h
+        self.buf["cpp"] = torch.zeros(self.k, (self.k + 15) // 16 * 16, dtype=torch.float64)
         return {"sums": self.sums, "centre": self.centre, "interact": self.interact, "drift": self.drift,
-                "update": self.update}
+                "update": self.update, "peek": self.peek, "cpp": self.cpp, "resolve": self.resolve}
 
     def sums(self):
         s = np.concatenate([self.G.sum(axis=1), self.U.sum(axis=1)])
@@ -65,20 +66,42 @@ class NumpyPhases(object):
         cuu[:] = 0.0
         cuu[:, :p] = C
 
-    def interact(self):
+    def _loops(self, W):
         p, k, c = self.p, self.k, self.cols
         e_all, ut_all = self.buf["e_all"].numpy(), self.buf["ut_all"].numpy()
-        self.C = self.buf["cuu"].numpy()[:, :p].copy()
         ssq = 0.0
         V = np.zeros((p, c))
         for s in range(self.nranks):
             Es = e_all[s * k:(s + 1) * k, :self.Jl]
             Uts = ut_all[s * p:(s + 1) * p, :self.Jl]
-            D = (Es.T @ self.W) / self.J
+            D = (Es.T @ W) / self.J
             ssq += (D ** 2).sum()
             V += Uts @ D
         self.V = V
-        self.buf["scalars"][0, 0] = ssq
+        return ssq
+
+    def interact(self, skip=False):
+        self.C = self.buf["cuu"].numpy()[:, :self.p].copy()
+        if not skip:
+            self.buf["scalars"][0, 0] = self._loops(self.W)
+
+    def peek(self):
+        S = self.buf["scalars"][0].numpy()
+        self.h_kept = self.fixed_h if self.fixed_h is not None else 1.0 / (np.sqrt(S[0]) + 1e-8)
+        return self.h_kept
+
+    def cpp(self):
+        k, c = self.k, self.cols
+        E = self.buf["e_all"].numpy()[self.rank * k:(self.rank + 1) * k, :c]
+        out = self.buf["cpp"].numpy()
+        out[:] = 0.0
+        out[:, :k] = (E @ E.T) / self.J
+
+    def resolve(self):
+        k = self.k
+        M = self.h_kept * self.buf["cpp"].numpy()[:, :k] + self.Gamma
+        R = self.G - self.y[:, None]
+        self._loops(np.linalg.solve(M, R))
 
     def drift(self):
         p, c = self.p, self.cols
@@ -87,7 +110,7 @@ class NumpyPhases(object):
         self.T = -self.V - self.C @ self.Z + self.switch * alpha * Ut
         self.buf["scalars"][0, 5] = np.abs(self.T).max() if c else 0.0
 
-    def update(self):
+    def update(self, keep=False):
         p, c = self.p, self.cols
         S = self.buf["scalars"][0].numpy()
         Ut = self.buf["ut_all"].numpy()[self.rank * p:(self.rank + 1) * p, :c]
@@ -96,7 +119,7 @@ class NumpyPhases(object):
             h = 0.1 / S[5]
             out = self.U + h * self.T + np.sqrt(2 * h) * (np.linalg.cholesky(self.C) @ self.xi)
         else:
-            h = 1.0 / (np.sqrt(S[0]) + 1e-8)
+            h = self.h_kept if keep else (self.fixed_h if self.fixed_h is not None else 1.0 / (np.sqrt(S[0]) + 1e-8))
             if self.rule == "aldi":
                 out = (self.U + h * alpha * Ut - h * self.V - h * (self.C @ self.Z)
                        + np.sqrt(2 * h) * (np.linalg.cholesky(self.C) @ self.xi))

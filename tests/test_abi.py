@@ -38,7 +38,7 @@ def test_invalid_arguments_are_rejected_without_touching_the_gpu():
     assert lib.ces_create(2, 5, 10, 10, 3, 2, 10, None, 0, ctypes.byref(h)) == _lib.CES_ERR_INVALID
     assert lib.ces_create(2, 5, 4, 10, 0, 2, 4, None, 0, ctypes.byref(h)) == _lib.CES_ERR_INVALID   # 2*4 < 10
     assert b"inconsistent" in lib.ces_last_error()
-    assert lib.ces_phase3_interact(None, 1) == _lib.CES_ERR_INVALID
+    assert lib.ces_phase3_interact(None, 1, 0) == _lib.CES_ERR_INVALID
     assert lib.ces_gemm(None, 7, 0, 4, 4, 4, 1.0, None, 4, None, 4, 0.0, None, 4) == _lib.CES_ERR_INVALID
     with pytest.raises(ValueError):
         _lib.check(_lib.CES_ERR_INVALID)

@@ -76,6 +76,23 @@ def test_step_parity_against_oracle(d, k, J, dense):
         eng.close()
 
 
+@pytest.mark.parametrize("d,k,J,dense", [(6, 9, 40, True), (20, 33, 150, False), (64, 130, 600, True)])
+def test_non_default_time_steps_match_oracle(d, k, J, dense):
+    """time_step='constant' / 'mix' with the hk C^pp + Gamma re-solve of D (ces/calibrate.py:439-441, 470-473)
+    through the reference-facing methods, against the oracle (itself pinned to the real reference for these modes)."""
+    pr = eo.linear_gaussian_problem(d, k, J, dense_gamma=dense)
+    for rule in ("aldi", "eks"):
+        for ts, t_hist in (("constant", []), ("constant", [0.4, 0.9]), ("mix", []), ("mix", [0.5, 1.7]), ("mix", [2.0, 5.0])):
+            s = _sampler(d, k, J, pr["mu"], pr["Sigma0"], pr["ustar"], t_hist)
+            s._ensure_metrics()
+            np.random.seed(1)
+            Uk = getattr(s, METHOD[rule])(pr["y"], pr["U0"], pr["G"], pr["Gamma"], 0, time_step=ts, delta_t=0.03)
+            o = eo.step(rule, pr["y"], pr["U0"], pr["G"], pr["Gamma"], pr["mu"], pr["Sigma0"], pr["ustar"], pr["xi"],
+                        time_step=ts, delta_t=0.03, T=s.T, t_last=t_hist[-1] if t_hist else None)
+            assert _rel(Uk, o["Uk"]) < TOL, (rule, ts, t_hist)
+            assert abs(s.metrics["t"][-1] - o["t"]) < TOL * o["t"], (rule, ts, t_hist)
+
+
 def test_device_resident_step_with_strided_tensors():
     """Engine.step on CUDA tensors that are column slices of wider buffers (leading dimension != J, odd
     offset so the noise operand needs the internal re-pack)."""

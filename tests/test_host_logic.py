@@ -34,14 +34,26 @@ def test_time_bookkeeping_matches_reference_rule():
     assert s.metrics["t"] == [0.5, 0.75]
 
 
-def test_unsupported_time_steps_are_refused_loudly():
+def test_time_step_kwargs_map_to_step_options():
+    """time_step semantics of ces/calibrate.py:247-260 (hk) and :439-441 / :470-473 (re-solve of D)."""
     s = calibrate.sampling(2, 3, 10)
-    for kind in ("constant", "mix", "spectral", "adaptive"):
+    s.T = 30
+    for kind in ("spectral", "adaptive"):
         with pytest.raises(NotImplementedError):
-            s._step_options({"time_step": kind})
+            s._step_options("aldi", {"time_step": kind})
     with pytest.raises(ValueError):
-        s._step_options({"time_step": "bogus"})
-    assert s._step_options({}) is None
+        s._step_options("aldi", {"time_step": "bogus"})
+    assert s._step_options("aldi", {}) == (None, None)
+    assert s._step_options("aldi", {"time_step": "constant"}) == (1. / 15, "always")
+    assert s._step_options("eks", {"time_step": "constant", "delta_t": 0.5}) == (0.5, "always")
+    assert s._step_options("aldi_constant", {"time_step": "constant"}) == (None, None)
+    s._ensure_metrics()
+    assert s._step_options("aldi", {"time_step": "mix"}) == (None, (0.0, 1.0))        # first step: default rule
+    s.metrics["t"] = [0.5, 2.0]
+    assert s._step_options("aldi", {"time_step": "mix"}) == (None, (2.0, 1.0))        # before spin-up (4.0)
+    assert s._step_options("eks", {"time_step": "mix"}) == (None, None)               # eks never re-solves for mix
+    s.metrics["t"] = [0.5, 4.5]
+    assert s._step_options("aldi", {"time_step": "mix", "delta_t": 0.1}) == (0.1, (4.5, 1.0))
 
 
 def test_save_load_round_trip(tmp_path):

@@ -1,0 +1,36 @@
+"""Timing of the batched Darcy forward model (BASELINE configs 2 and 4 shapes) on one B200."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ces_b200 import darcy as cdarcy  # noqa: E402
+from ces_b200.engine import Engine  # noqa: E402
+
+out = []
+for (N, p, J, scale) in [(64, 64, 1024, 1.0), (64, 64, 1024, 10.0), (128, 256, 8192, 1.0), (128, 256, 8192, 10.0)]:
+    m = cdarcy.model_trunc(Nmesh=N, p=p)
+    rng = np.random.default_rng(0)
+    m.obs_index = rng.choice(N * N, size=50, replace=False)
+    U = torch.from_numpy(scale * rng.standard_normal((p, J))).cuda()
+    G = torch.empty(50, J, dtype=torch.float64, device="cuda")
+    eng = Engine(p, 50, J)
+    for _ in range(2):
+        m.evaluate_ensemble(eng, U, G)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        m.evaluate_ensemble(eng, U, G)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    r = dict(N=N, p=p, J=J, prior_scale=scale, ms=ms, members_per_s=J / ms * 1e3, cg_iterations=m.last_iterations)
+    print(r, flush=True)
+    out.append(r)
+    eng.close()
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(out, open("gpurun_out/bench_darcy.json", "w"), indent=1)
