@@ -36,10 +36,11 @@ __device__ __forceinline__ double block_sum_512(double v, double* scratch) {
     __syncthreads();
     if (lane == 0) scratch[wid] = v;
     __syncthreads();
-    double t = 0.0;
+    // every thread adds the 16 warp partials as the same balanced tree (depth 4 instead of a 16-long chain)
+    double v8[8];
 #pragma unroll
-    for (int w = 0; w < PCG_THREADS / 32; ++w) t += scratch[w];   // every thread sums in the same order
-    return t;
+    for (int w = 0; w < 8; ++w) v8[w] = scratch[2 * w] + scratch[2 * w + 1];
+    return ((v8[0] + v8[1]) + (v8[2] + v8[3])) + ((v8[4] + v8[5]) + (v8[6] + v8[7]));
 }
 
 // One cluster (gridDim.x = members * C, cluster dims (C,1,1)) solves one member.
@@ -55,6 +56,7 @@ darcy_pcg_kernel(const double* __restrict__ cn, double* __restrict__ pn, int K, 
     extern __shared__ double smem[];
     double* cs = smem;                              // (R + 2) x K  nodal coefficients, rows r0-1 .. r0+R
     double* ps = cs + (size_t)(R + 2) * K;          // (R + 2) x K  search direction with halos
+    double* zh = ps + (size_t)(R + 2) * K;          // 2 x K        z rows pushed by the neighbouring CTAs
     __shared__ PcgShared sh;
     __shared__ double scratch[PCG_THREADS / 32];
 
@@ -72,7 +74,9 @@ darcy_pcg_kernel(const double* __restrict__ cn, double* __restrict__ pn, int K, 
         cs[idx] = (rr <= K - 1) ? cfield[(size_t)rr * K + idx % K] : 0.0;
         ps[idx] = 0.0;
     }
-    __syncthreads();
+    for (int idx = threadIdx.x; idx < 2 * K; idx += PCG_THREADS) zh[idx] = 0.0;
+    if (threadIdx.x < 32) (&sh.red[0][0][0])[threadIdx.x] = 0.0;
+    cluster.sync();                                 // zh is cleared everywhere before any neighbour pushes into it
 
     // ---- per-node data in registers
     double wN[4], wS[4], wWE[5], invd[4], x[4], r[4], p[4];
@@ -109,45 +113,70 @@ darcy_pcg_kernel(const double* __restrict__ cn, double* __restrict__ pn, int K, 
     for (int q = 0; q < 4; ++q) { p[q] = r[q] * invd[q]; rz_loc += r[q] * p[q]; }
 
     double* prow = ps + (size_t)((active ? qrow : 0) + 1) * K + j0;
-    double* north_halo = nullptr;   // neighbour's south-halo row (we are its north... see below)
-    double* south_halo = nullptr;
-    if (crank > 0) north_halo = cluster.map_shared_rank(ps, crank - 1) + (size_t)(R + 1) * K;   // rank-1's bottom halo = our first row
-    if (crank < C - 1) south_halo = cluster.map_shared_rank(ps, crank + 1);                      // rank+1's top halo = our last row
+    // Halo protocol (two cluster barriers per iteration instead of three): a CTA never sends p.  It pushes the first /
+    // last row of z = M^-1 r into the neighbour's `zh` rows right before the barrier of the r.z reduction, and after
+    // that barrier every CTA updates its own copy of the neighbour's p row with the same p = z + beta p the owner
+    // executes (bit-identical), so the search direction needs no exchange of its own.
+    double* zh_n = zh + j0;                 // z of the row above this strip (written by rank-1)
+    double* zh_s = zh + K + j0;             // z of the row below (written by rank+1)
+    double* push_n = (crank > 0) ? cluster.map_shared_rank(zh, crank - 1) + K + j0 : nullptr;   // our first row = its south halo
+    double* push_s = (crank < C - 1) ? cluster.map_shared_rank(zh, crank + 1) + j0 : nullptr;   // our last row = its north halo
+    const bool first_row = active && qrow == 0, last_row = active && qrow == R - 1;
 
-    auto publish_p = [&]() {
-        if (active) {
-            *reinterpret_cast<double2*>(prow) = make_double2(p[0], p[1]);
-            *reinterpret_cast<double2*>(prow + 2) = make_double2(p[2], p[3]);
-            if (qrow == 0 && north_halo) {
-                *reinterpret_cast<double2*>(north_halo + j0) = make_double2(p[0], p[1]);
-                *reinterpret_cast<double2*>(north_halo + j0 + 2) = make_double2(p[2], p[3]);
-            }
-            if (qrow == R - 1 && south_halo) {
-                *reinterpret_cast<double2*>(south_halo + j0) = make_double2(p[0], p[1]);
-                *reinterpret_cast<double2*>(south_halo + j0 + 2) = make_double2(p[2], p[3]);
-            }
+    auto push_z = [&](const double (&z)[4]) {
+        if (first_row && push_n) {
+            *reinterpret_cast<double2*>(push_n) = make_double2(z[0], z[1]);
+            *reinterpret_cast<double2*>(push_n + 2) = make_double2(z[2], z[3]);
+        }
+        if (last_row && push_s) {
+            *reinterpret_cast<double2*>(push_s) = make_double2(z[0], z[1]);
+            *reinterpret_cast<double2*>(push_s + 2) = make_double2(z[2], z[3]);
         }
     };
-    int parity = 0;
     // Cluster-wide sum: every CTA pushes its block partial into slot [crank] of every CTA (remote stores are
     // fire-and-forget), one cluster barrier, then each thread adds the C local slots in rank order -- the same
     // order on every CTA, so all of them take identical decisions.
+    int parity = 0;
     auto cluster_dot = [&](double local, int which) -> double {
         const double b = block_sum_512(local, scratch);
         if ((int)threadIdx.x < C) cluster.map_shared_rank(&sh, threadIdx.x)->red[parity][which][crank] = b;
         cluster.sync();
-        double t = 0.0;
-        for (int c = 0; c < C; ++c) t += sh.red[parity][which][c];
-        return t;
+        // unused slots stay zero (static shared memory is not cleared: see the init below), fixed tree order
+        const double* rr = sh.red[parity][which];
+        return ((rr[0] + rr[1]) + (rr[2] + rr[3])) + ((rr[4] + rr[5]) + (rr[6] + rr[7]));
     };
 
-    publish_p();
-    double rz = cluster_dot(rz_loc, 0);    // the sync inside also makes the halos of p visible
+    double z[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) z[q] = p[q];        // z0 = M^-1 r0 (computed above into p)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) p[q] = 0.0;
+    push_z(z);
+    double rz = cluster_dot(rz_loc, 0);     // the barrier inside also makes the z halos visible
     parity ^= 1;
     const double rz0 = rz;
+    double beta = 0.0;
     int it = 0;
     if (rz0 > 0.0) {
         for (it = 0; it < max_iter; ++it) {
+            // ---- p = z + beta p: own quad, and this CTA's copies of the neighbouring rows
+            if (active) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) p[q] = z[q] + beta * p[q];
+                *reinterpret_cast<double2*>(prow) = make_double2(p[0], p[1]);
+                *reinterpret_cast<double2*>(prow + 2) = make_double2(p[2], p[3]);
+                if (first_row && crank > 0) {
+                    double* hp = prow - K;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) hp[q] = zh_n[q] + beta * hp[q];
+                }
+                if (last_row && crank < C - 1) {
+                    double* hp = prow + K;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) hp[q] = zh_s[q] + beta * hp[q];
+                }
+            }
+            __syncthreads();
             // ---- ap = A p
             double ap[4] = {0.0, 0.0, 0.0, 0.0}, pap_loc = 0.0;
             if (active) {
@@ -168,7 +197,7 @@ darcy_pcg_kernel(const double* __restrict__ cn, double* __restrict__ pn, int K, 
             }
             const double pap = cluster_dot(pap_loc, 0);
             const double alpha = rz / pap;
-            double rz_new_loc = 0.0, z[4];
+            double rz_new_loc = 0.0;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 x[q] += alpha * p[q];
@@ -176,15 +205,12 @@ darcy_pcg_kernel(const double* __restrict__ cn, double* __restrict__ pn, int K, 
                 z[q] = r[q] * invd[q];
                 rz_new_loc += r[q] * z[q];
             }
+            push_z(z);
             const double rz_new = cluster_dot(rz_new_loc, 1);
             parity ^= 1;
             if (rz_new <= tol2 * rz0) { ++it; break; }
-            const double beta = rz_new / rz;
+            beta = rz_new / rz;
             rz = rz_new;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) p[q] = z[q] + beta * p[q];
-            publish_p();
-            cluster.sync();      // new p and its halos visible everywhere before the next stencil
         }
     }
     // ---- write the nodal pressure (boundary stays zero: the buffer is cleared beforehand)
@@ -220,7 +246,7 @@ struct DarcyModel {
 
 static int pcg_launch(DarcyModel* m, const double* cn, double* pn, int members, double tol, int max_iter) {
     const int K = m->N;
-    const size_t smem = (size_t)2 * (m->R + 2) * K * sizeof(double);
+    const size_t smem = ((size_t)2 * (m->R + 2) + 2) * K * sizeof(double);
     static size_t configured = 0;
     if (smem > configured) {
         CES_CUDA(cudaFuncSetAttribute(darcy_pcg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
