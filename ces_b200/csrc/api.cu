@@ -37,6 +37,9 @@ struct ces_handle_s {
     double *stage_U = nullptr, *stage_G = nullptr, *stage_xi = nullptr, *stage_out = nullptr;
     double* pending_out = nullptr;      // host destination of stage_out, copied inside phase 4 before its final sync
     int64_t pending_rows = 0;
+    cudaStream_t aux_st = nullptr;      // chol(C^uu) runs here, hidden behind the D / V GEMMs of the main stream
+    cudaEvent_t cuu_ready = nullptr, chol_done = nullptr;
+    bool chol_pending = false;
     cudaStream_t copy_st = nullptr;     // uploads xi while phases 1-3 run
     cudaEvent_t copy_ev = nullptr, start_ev = nullptr;
     std::vector<void*> allocs;
@@ -198,8 +201,13 @@ int ces_create(int64_t p, int64_t k, int64_t J_local, int64_t J_global, int rank
 int ces_destroy(ces_handle_t h) {
     if (!h) return CES_OK;
     cudaStreamSynchronize(h->st);
+    if (h->aux_st) cudaStreamSynchronize(h->aux_st);
+    if (h->copy_st) cudaStreamSynchronize(h->copy_st);
     for (void* ptr : h->allocs) cudaFree(ptr);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    if (h->cuu_ready) cudaEventDestroy(h->cuu_ready);
+    if (h->chol_done) cudaEventDestroy(h->chol_done);
+    if (h->aux_st) cudaStreamDestroy(h->aux_st);
     if (h->copy_ev) cudaEventDestroy(h->copy_ev);
     if (h->start_ev) cudaEventDestroy(h->start_ev);
     if (h->copy_st) cudaStreamDestroy(h->copy_st);
@@ -382,11 +390,24 @@ int ces_phase3_interact(ces_handle_t h, int rule, int skip_interaction) {
     if (rule != h->last_rule) return fail(CES_ERR_STATE, "phase3: rule differs from phase2%s", "");
     const int64_t p = h->p;
     cudaStream_t st = h->st;
-    // chol(C^uu)  (K7); EKI has no noise term and skips it
+    // chol(C^uu)  (K7); EKI has no noise term and skips it.  Only the noise GEMM of phase 4 needs the factor, so it
+    // is computed on a high-priority side stream while the main stream runs the D and V GEMMs (its ~50 small
+    // launches would otherwise sit on the critical path: 3 % of a cfg3 step).
     if (rule != CES_RULE_EKI) {
+        if (!h->aux_st) {
+            int lo = 0, hi = 0;
+            CES_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CES_CUDA(cudaStreamCreateWithPriority(&h->aux_st, cudaStreamNonBlocking, hi));
+            CES_CUDA(cudaEventCreateWithFlags(&h->cuu_ready, cudaEventDisableTiming));
+            CES_CUDA(cudaEventCreateWithFlags(&h->chol_done, cudaEventDisableTiming));
+        }
+        CES_CUDA(cudaEventRecord(h->cuu_ready, st));
+        CES_CUDA(cudaStreamWaitEvent(h->aux_st, h->cuu_ready, 0));
         CES_CUDA(cudaMemcpy2DAsync(h->L, h->ldp * sizeof(double), h->Cuu, h->ldp * sizeof(double), p * sizeof(double), p,
-                                   cudaMemcpyDeviceToDevice, st));
-        CES_TRY(potrf_lower(st, h->L, h->ldp, p, h->Linv, kLinvLd, h->info));
+                                   cudaMemcpyDeviceToDevice, h->aux_st));
+        CES_TRY(potrf_lower(h->aux_st, h->L, h->ldp, p, h->Linv, kLinvLd, h->info));
+        CES_CUDA(cudaEventRecord(h->chol_done, h->aux_st));
+        h->chol_pending = true;
     }
     if (skip_interaction) return CES_OK;       // 'constant' step size: D is formed once, by ces_phase3c_resolve
     return interaction_loops(h, h->W, true);
@@ -501,6 +522,10 @@ int ces_phase4_update(ces_handle_t h, int rule, int ts_kind, double fixed_h, con
         xi_use = h->xi_pad; ldxi_use = ld;
     }
 
+    if (h->chol_pending) {              // the factor of C^uu from the side stream
+        CES_CUDA(cudaStreamWaitEvent(st, h->chol_done, 0));
+        h->chol_pending = false;
+    }
     const int kind = (rule == CES_RULE_ALDI_CONSTANT) ? 2 : (ts_kind == CES_TS_FIXED ? 1 : 0);
     if (ts_kind != CES_TS_KEEP || rule == CES_RULE_ALDI_CONSTANT) CES_TRY(step_scalars(st, S, kind, fixed_h, alphaJ));
 
