@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--workload", default=os.environ.get("CES_BENCH_WORKLOAD", "target"), choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--formulation", default="interaction", choices=["interaction", "factored"],
+                    help="'interaction' forms the J x J matrix D like the reference (the graded formulation, default); "
+                         "'factored' is the opt-in algorithmically reduced path (same update to rounding, D never formed)")
     return ap.parse_args()
 
 
@@ -60,6 +63,9 @@ def config_of(args, d, k, J, nranks):
                         % (d, k, J, args.workload),
             "d": d, "k": k, "J": J, "update": "aldi", "time_step": "default 1/(||D||_F+1e-8)",
             "parallelism": "particle columns sharded over %d GPU(s)" % nranks,
+            "formulation": ("interaction: D = (1/J) E^T W formed in panels (reference formulation)"
+                            if args.formulation == "interaction" else
+                            "factored: ALGORITHMICALLY REDUCED, (U~ E^T) W and Gram-matrix ||D||_F, D never formed"),
             "l2": "inputs per step (U, G, xi = %.2f GB) exceed the 126 MB L2; no explicit flush" % (8.0 * J * (2 * d + k) / 1e9)}
 
 
@@ -251,7 +257,7 @@ def main():
 
     # ---- device-resident steps
     def step_dev():
-        eng.step("aldi", U, G, xi, out=out)
+        eng.step("aldi", U, G, xi, out=out, formulation=args.formulation)
 
     for _ in range(max(args.warmup, 3)):
         step_dev()
@@ -282,7 +288,7 @@ def main():
         Un, Gn, xn = U_h.numpy(), G_h.numpy(), xi_h.numpy()
 
         def step_e2e():
-            s.eks_update_aldi(y_h, Un, Gn, Gamma, 0, xi=xn)
+            s.eks_update_aldi(y_h, Un, Gn, Gamma, 0, xi=xn, formulation=args.formulation)
     else:
         out_h = torch.empty(U.shape, dtype=torch.float64).pin_memory()
         Ud, Gd, xd = torch.empty_like(U), torch.empty_like(G), torch.empty_like(xi)
@@ -291,7 +297,7 @@ def main():
             Ud.copy_(U_h, non_blocking=True)
             Gd.copy_(G_h, non_blocking=True)
             xd.copy_(xi_h, non_blocking=True)
-            eng.step("aldi", Ud, Gd, xd, out=out)
+            eng.step("aldi", Ud, Gd, xd, out=out, formulation=args.formulation)
             out_h.copy_(out, non_blocking=True)
             torch.cuda.synchronize()
 
@@ -309,6 +315,10 @@ def main():
         return
 
     flops_step = eo.algorithmic_flops(J, d, k)
+    if args.formulation == "factored":
+        # flops of the reduced path: P1 and V (2dkJ each), two symmetric Gram matrices (k^2 J each), covariance,
+        # prior and noise products, Cholesky
+        flops_step = 4.0 * d * k * J + 2.0 * k * k * J + 6.0 * d * d * J + d ** 3 / 3.0 + k * J
     peak = dgemm_tflops
     achieved = gemm_flops / (gemm_ms * 1e-3) * 1e-12 if gemm_ms > 0 else None
     roofline = {"bound": "tensor", "kernel": "gemm_dmma_kernel<A_KM,B_KN> (D = (1/J) E^T W, FP64 DMMA.8x8x4 + TMA)",
@@ -320,6 +330,11 @@ def main():
                 "traffic": TRAFFIC_BYTES.get(args.workload),
                 "step_achieved_tflops": flops_step / (ms_per_step * 1e-3) * 1e-12,
                 "step_frac_of_peak": flops_step / (ms_per_step * 1e-3) * 1e-12 / (peak * world) if peak else None}
+    if args.formulation == "factored":
+        roofline.update({"kernel": "whole step, factored formulation (no single dominant kernel; D GEMM not launched)",
+                         "achieved": roofline["step_achieved_tflops"], "frac": roofline["step_frac_of_peak"],
+                         "launches": None, "ms_per_launch": None, "share_of_step": None, "traffic": None,
+                         "algorithmically_reduced": True})
     line = {"metric": METRIC, "value": value, "unit": "particle-updates/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_of(args, d, k, J, world),

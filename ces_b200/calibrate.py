@@ -18,6 +18,9 @@ ces/calibrate.py:404-416).  What differs is where the arithmetic runs:
 * Noise: by default ``xi = np.random.normal(0, 1, [p, J])`` is drawn from the global
   numpy RNG at the point where the reference draws it (ces/calibrate.py:447,488,527),
   so a seeded script consumes the same random stream.
+* ``formulation='factored'`` (kwarg of ``run`` / ``eks_update*`` or attribute; default ``'interaction'``) computes
+  the same update without forming the J x J matrix D: ``(U - ubar) D = (1/J) ((U - ubar) E^T) W`` and ``||D||_F`` from
+  two k x k Gram matrices -- identical to rounding (~1e-15), ``O(d k J + k^2 J)`` instead of ``O((k + d) J^2)``.
 * Multi-GPU: if ``self.group`` is a ``torch.distributed`` process group, every rank
   calls ``run`` with the same arguments and the ensemble is sharded by particle
   columns.
@@ -282,7 +285,8 @@ class sampling(enka):
         if rule != 'eki':
             xi = self._draw_noise(U0.shape, kwargs)
         Uk, hk, met = eng.step_host(rule, U0, np.asarray(Geval, dtype=np.float64)[:self.n_obs], xi, fixed_h=fixed,
-                                    switch=kwargs.get('switch', 1.), resolve=resolve)
+                                    switch=kwargs.get('switch', 1.), resolve=resolve,
+                                    formulation=kwargs.get('formulation', getattr(self, 'formulation', 'interaction')))
         self._record(met, hk)
         return Uk
 
@@ -389,7 +393,8 @@ class sampling(enka):
                     xi_dev = torch.from_numpy(np.ascontiguousarray(xi[:, lo:hi])).to(dev)
                 fixed, resolve = self._step_options(rule, kwargs)     # 'mix' depends on the time reached so far
                 U_dev, hk, met = eng.step(rule, U_dev, G_cur, xi_dev, fixed_h=fixed, switch=kwargs.get('switch', 1.),
-                                          resolve=resolve)
+                                          resolve=resolve,
+                                          formulation=kwargs.get('formulation', getattr(self, 'formulation', 'interaction')))
                 self._record(met, hk)
             # an unknown ``update`` leaves the ensemble unchanged and records nothing, like :364-369 --
             # the reference then fails on the empty ``metrics['t']``; so do we

@@ -27,6 +27,9 @@ struct ces_handle_s {
     int64_t ssq_cap = 0, splitk_cap = 0;
     int syrk_splits = 1;
     int* info = nullptr;
+    // factored formulation (D never formed): P1 = U~ E^T, Gram matrices of E and W
+    double *P1 = nullptr, *GE = nullptr, *GW = nullptr, *gram_ws = nullptr, *gram_part = nullptr;
+    int gram_splits = 1, p1_splits = 1;
     // K11 (time_step 'constant' / 'mix'): D re-solved with Gamma -> h*C^pp + Gamma
     std::vector<double> gamma_host;
     double *GammaD = nullptr, *Cpp = nullptr, *Mk = nullptr, *MkLinv = nullptr, *MkInv = nullptr, *Wr = nullptr, *cpp_ws = nullptr;
@@ -481,6 +484,91 @@ int ces_phase3c_resolve(ces_handle_t h, int rule) {
     return interaction_loops(h, h->Wr, false);
 }
 
+// ---- factored formulation: the same update without forming the J x J matrix -------------------------------------
+//   V = U~ D = (1/J) (U~ E^T) W         (d x k) then (d x J):  4 d k J flops instead of 2 (k + d) J^2
+//   ||D||_F^2 = sum((E E^T) o (W W^T)) / J^2          two k x k Gram matrices:  ~2 k^2 J flops (symmetric halves)
+// Phase 3f-a forms the local parts of P1 = U~ E^T, GE = E E^T, GW = W W^T over this rank's columns
+// [host: all-reduce(sum) of "p1", "gram_e", "gram_w"]; phase 3f-b finishes V and the sum of squares.
+__global__ void __launch_bounds__(256) gram_dot_kernel(const double* __restrict__ A, const double* __restrict__ B, long long ld,
+                                                       int n, double scale, double* __restrict__ part) {
+    __shared__ double scratch[32];
+    const int i = blockIdx.x;
+    double a = 0.0;
+    for (int j = threadIdx.x; j < n; j += 256) a += A[(size_t)i * ld + j] * B[(size_t)i * ld + j];
+    const double t = block_sum(a, scratch);
+    if (threadIdx.x == 0) part[i] = t * scale;
+}
+
+int ces_phase3f_products(ces_handle_t h, int rule) {
+    CES_TRY(valid(h, true));
+    if (rule != h->last_rule) return fail(CES_ERR_STATE, "phase3f: rule differs from phase2%s", "");
+    const int64_t p = h->p, k = h->k, ld = h->ldJ;
+    cudaStream_t st = h->st;
+    if (!h->P1) {
+        const int64_t tm = ceil_div(k, GEMM_BM), lower = tm * (tm + 1) / 2;
+        int64_t sp = ceil_div(296, lower);
+        const int64_t kb = ceil_div(ld, GEMM_BK);
+        if (sp > kb) sp = kb;
+        if (sp > 64) sp = 64;
+        if (sp < 1) sp = 1;
+        h->gram_splits = (int)sp;
+        // P1 has few (d/128 x k/128) tiles and a long contraction: split it so the tiles fill the machine
+        int64_t sp1 = ceil_div(296, ceil_div(p, GEMM_BM) * ceil_div(k, GEMM_BN));
+        if (sp1 > kb) sp1 = kb;
+        if (sp1 > 64) sp1 = 64;
+        if (sp1 < 1) sp1 = 1;
+        h->p1_splits = (int)sp1;
+        const int64_t ws = sp * k * k > sp1 * p * k ? sp * k * k : sp1 * p * k;
+        CES_TRY(dalloc(h, &h->P1, p * h->ldk));
+        CES_TRY(dalloc(h, &h->GE, k * h->ldk));
+        CES_TRY(dalloc(h, &h->GW, k * h->ldk));
+        CES_TRY(dalloc(h, &h->gram_ws, ws));
+        CES_TRY(dalloc(h, &h->gram_part, k));
+    }
+    // chol(C^uu) on the side stream, as in ces_phase3_interact
+    CES_TRY(ces_phase3_interact(h, rule, 1));
+    const double* E = e_block(h, h->rank);
+    const double* Ut = ut_block(h, h->rank);
+    GemmCall g;                                  // P1 = U~ E^T  (d x k), contraction over the local particles
+    g.a_mode = A_MK; g.b_mode = B_NK;
+    g.M = (int)p; g.N = (int)k; g.K = (int)h->Jl;
+    g.A = Ut; g.lda = ld; g.B = E; g.ldb = ld; g.C = h->P1; g.ldc = h->ldk;
+    g.splits = h->p1_splits; g.splitk_ws = h->gram_ws;
+    CES_TRY(gemm(st, g));
+    for (int which = 0; which < 2; ++which) {   // GE = E E^T, GW = W W^T (lower tiles, mirrored)
+        GemmCall s2;
+        s2.a_mode = A_MK; s2.b_mode = B_NK;
+        s2.M = (int)k; s2.N = (int)k; s2.K = (int)h->Jl;
+        s2.A = which == 0 ? E : h->W; s2.lda = ld; s2.B = s2.A; s2.ldb = ld;
+        s2.C = which == 0 ? h->GE : h->GW; s2.ldc = h->ldk;
+        s2.flags = GEMM_C_LOWER_ONLY;
+        s2.splits = h->gram_splits; s2.splitk_ws = h->gram_ws;
+        CES_TRY(gemm(st, s2));
+    }
+    return CES_OK;
+}
+
+int ces_phase3f_finish(ces_handle_t h, int rule) {
+    CES_TRY(valid(h, true));
+    if (rule != h->last_rule || !h->P1) return fail(CES_ERR_STATE, "phase3f_finish: ces_phase3f_products has not run%s", "");
+    const int64_t p = h->p, k = h->k, ld = h->ldJ;
+    cudaStream_t st = h->st;
+    const double invJ = 1.0 / (double)h->Jg;
+    GemmCall g;                                  // V = (1/J) P1 W
+    g.a_mode = A_MK; g.b_mode = B_KN;
+    g.M = (int)p; g.N = (int)h->Jl; g.K = (int)k;
+    g.A = h->P1; g.lda = h->ldk; g.B = h->W; g.ldb = ld; g.C = h->V; g.ldc = ld;
+    g.alpha = invJ;
+    CES_TRY(gemm(st, g));
+    // ||D||_F^2 = sum_ab GE_ab GW_ab / J^2.  Every rank holds the all-reduced Gram matrices, so the value is global:
+    // only rank 0 contributes it to the scalar that the host all-reduces afterwards.
+    gram_dot_kernel<<<(unsigned)k, 256, 0, st>>>(h->GE, h->GW, h->ldk, (int)k, invJ * invJ, h->gram_part);
+    CES_LAUNCHED(1);
+    if (h->rank == 0) CES_TRY(sum_vector(st, h->gram_part, k, h->S + S_SSQ));
+    else CES_CUDA(cudaMemsetAsync(h->S + S_SSQ, 0, sizeof(double), st));
+    return CES_OK;
+}
+
 int ces_phase4a_drift(ces_handle_t h, double switch_) {
     CES_TRY(valid(h, true));
     if (h->last_rule != CES_RULE_ALDI_CONSTANT) return fail(CES_ERR_STATE, "phase4a is for aldi_constant only%s", "");
@@ -729,6 +817,9 @@ int ces_buffer(ces_handle_t h, const char* name, double** ptr, int64_t* rows, in
     else if (n == "w") { q = h->W; r = h->k; c = h->ldJ; l = h->ldJ; }
     else if (n == "v") { q = h->V; r = h->p; c = h->ldJ; l = h->ldJ; }
     else if (n == "z") { q = h->Z; r = h->p; c = h->ldJ; l = h->ldJ; }
+    else if (n == "p1") { q = h->P1; r = h->p; c = h->ldk; l = h->ldk; }
+    else if (n == "gram_e") { q = h->GE; r = h->k; c = h->ldk; l = h->ldk; }
+    else if (n == "gram_w") { q = h->GW; r = h->k; c = h->ldk; l = h->ldk; }
     else if (n == "cpp") { q = h->Cpp; r = h->k; c = h->ldk; l = h->ldk; }
     else if (n == "d_panel") { q = h->D; r = h->ldJ; c = h->ldD; l = h->ldD; }
     else return fail(CES_ERR_INVALID, "ces_buffer: unknown buffer '%s'", name);

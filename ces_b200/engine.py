@@ -26,7 +26,7 @@ def shard_range(J, rank, nranks):
     return lo, min(J, lo + w)
 
 
-def run_phases(phases, buffer, comm, p, k, rule, resolve=None):
+def run_phases(phases, buffer, comm, p, k, rule, resolve=None, formulation="interaction"):
     """One update as phases with the collectives of a column-sharded ensemble in between
     (include/ces_b200.h).  ``comm`` is None on a single GPU, else ``(dist, group, rank)``:
 
@@ -37,6 +37,10 @@ def run_phases(phases, buffer, comm, p, k, rule, resolve=None):
         [peek -> cpp -> all-reduce(sum) "cpp" (k x ldk) -> resolve]      non-default time_step only (K11)
         drift     -> all-reduce(max)  "scalars"[5:6]                     aldi_constant only
         update
+
+    ``formulation``: "interaction" forms D = (1/J) E^T W in panels (the reference's formulation, the default);
+    "factored" computes the same V = U~ D as (1/J)(U~ E^T) W and ||D||_F through two k x k Gram matrices, with
+    all-reduces of "p1", "gram_e", "gram_w" instead of the all-gathers (opt-in).
 
     ``resolve``: None (default step size rule), "always" ('constant': D is formed once, with
     hk C^pp + Gamma), or ``(t_last, threshold)`` ('mix': re-solve when t_last + hk > threshold,
@@ -65,12 +69,23 @@ def run_phases(phases, buffer, comm, p, k, rule, resolve=None):
     phases["sums"]()
     allreduce(buffer("sums") if comm is not None else None)
     phases["centre"]()
-    if comm is not None:
-        allreduce(buffer("cuu"))
-        e_all, ut_all = buffer("e_all"), buffer("ut_all")
-        dist.all_gather_into_tensor(e_all, e_all[rank * k:(rank + 1) * k].clone(), group=group)
-        dist.all_gather_into_tensor(ut_all, ut_all[rank * p:(rank + 1) * p].clone(), group=group)
-    phases["interact"](resolve == "always")
+    if formulation == "factored":
+        if resolve is not None:
+            raise NotImplementedError("the factored formulation supports the default step-size rule only")
+        if comm is not None:
+            allreduce(buffer("cuu"))
+        phases["products"]()
+        if comm is not None:
+            for name in ("p1", "gram_e", "gram_w"):
+                allreduce(buffer(name))
+        phases["finish_factored"]()
+    else:
+        if comm is not None:
+            allreduce(buffer("cuu"))
+            e_all, ut_all = buffer("e_all"), buffer("ut_all")
+            dist.all_gather_into_tensor(e_all, e_all[rank * k:(rank + 1) * k].clone(), group=group)
+            dist.all_gather_into_tensor(ut_all, ut_all[rank * p:(rank + 1) * p].clone(), group=group)
+        phases["interact"](resolve == "always")
     if comm is not None:
         allreduce_slice(buffer("scalars"), 0, 5)
     keep = False
@@ -190,7 +205,7 @@ class Engine(object):
         return ctypes.c_void_p(t.data_ptr()), int(t.stride(0))
 
     # ------------------------------------------------------------------ one update
-    def step(self, rule, U, G, xi, out=None, fixed_h=None, switch=1.0, resolve=None):
+    def step(self, rule, U, G, xi, out=None, fixed_h=None, switch=1.0, resolve=None, formulation="interaction"):
         """One update on this rank's columns.  U (p, cols), G (k, cols), xi (p, cols) are float64 CUDA
         tensors; returns (U_next, hk, metrics dict).  ``fixed_h`` gives the step size ('constant', 'mix' after
         spin-up); ``resolve`` asks for the hk C^pp + Gamma re-solve of D (see ``run_phases``)."""
@@ -208,7 +223,9 @@ class Engine(object):
         else:
             Xp, ldx = ctypes.c_void_p(0), 0
         lib, h = self.lib, self.h
-        if self.nranks == 1 and resolve is None:
+        if formulation not in ("interaction", "factored"):
+            raise ValueError("formulation must be 'interaction' or 'factored'")
+        if self.nranks == 1 and resolve is None and formulation == "interaction":
             _lib.check(lib.ces_step(h, r, ts, fh, float(switch), Up, ldu, Gp, ldg, Xp, ldx, Op, ldo,
                                     ctypes.byref(self._hk), self._met))
         else:
@@ -224,26 +241,28 @@ class Engine(object):
                 "peek": peek,
                 "cpp": lambda: _lib.check(lib.ces_phase3b_cpp(h)),
                 "resolve": lambda: _lib.check(lib.ces_phase3c_resolve(h, r)),
+                "products": lambda: _lib.check(lib.ces_phase3f_products(h, r)),
+                "finish_factored": lambda: _lib.check(lib.ces_phase3f_finish(h, r)),
                 "drift": lambda: _lib.check(lib.ces_phase4a_drift(h, float(switch))),
                 "update": lambda keep: _lib.check(lib.ces_phase4_update(
                     h, r, _lib.TS_KEEP if keep else ts, fh, Up, ldu, Xp, ldx, Op, ldo, ctypes.byref(self._hk), self._met)),
             }
             comm = (self.dist, self.group, self.rank) if self.nranks > 1 else None
-            run_phases(phases, self.buffer, comm, self.p, self.k, rule, resolve)
+            run_phases(phases, self.buffer, comm, self.p, self.k, rule, resolve, formulation)
         met = {key: float(self._met[i]) for i, key in enumerate(_METRIC_KEYS)}
         return out, float(self._hk.value), met
 
-    def step_host(self, rule, U, G, xi, fixed_h=None, switch=1.0, resolve=None):
+    def step_host(self, rule, U, G, xi, fixed_h=None, switch=1.0, resolve=None, formulation="interaction"):
         """The same update on host numpy arrays (single GPU): the copies to and from the device are part
         of the call.  This is what ``sampling.eks_update*`` invoke."""
         if self.nranks != 1:
             raise RuntimeError("step_host is single-GPU; shard device tensors and call step()")
-        if resolve is not None:
-            # non-default time_step: the phase-by-phase device path, with explicit copies around it
+        if resolve is not None or formulation != "interaction":
+            # non-default time_step / formulation: the phase-by-phase device path, with explicit copies around it
             torch = self.torch
             dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
             out, hk, met = self.step(rule, dev(U), dev(G), dev(xi) if xi is not None else None, fixed_h=fixed_h,
-                                     switch=switch, resolve=resolve)
+                                     switch=switch, resolve=resolve, formulation=formulation)
             return out.cpu().numpy(), hk, met
         r = _lib.RULES[rule]
         ts = _lib.TS_FIXED if fixed_h is not None else _lib.TS_FROBENIUS

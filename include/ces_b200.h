@@ -103,6 +103,13 @@ int ces_phase3_interact(ces_handle_t h, int rule, int skip_interaction);
 int ces_peek_step_size(ces_handle_t h, int ts_kind, double fixed_h, double* hk_host);
 int ces_phase3b_cpp(ces_handle_t h);
 int ces_phase3c_resolve(ces_handle_t h, int rule);
+/* Factored formulation (opt-in; the same update to rounding without forming the J x J matrix):
+ *   V = (1/J) (U~ E^T) W   and   ||D||_F^2 = sum((E E^T) o (W W^T)) / J^2.
+ * ces_phase3f_products replaces phase 3: local parts of P1 = U~ E^T (d x k), GE = E E^T, GW = W W^T (k x k)
+ * [host: all-reduce(sum) of ces_buffer "p1", "gram_e", "gram_w"]; ces_phase3f_finish forms V and the sum of squares
+ * [host: all-reduce(sum) of scalars[0:5] as after phase 3].  No all-gather of E / U~ is needed in this form. */
+int ces_phase3f_products(ces_handle_t h, int rule);
+int ces_phase3f_finish(ces_handle_t h, int rule);
 int ces_phase4a_drift(ces_handle_t h, double switch_);
 int ces_phase4_update(ces_handle_t h, int rule, int ts_kind, double fixed_h, const double* U_dev, int64_t ldu,
                       const double* xi_dev, int64_t ldxi, double* Uout_dev, int64_t ldo, double* hk_host,

@@ -32,9 +32,14 @@ class NumpyPhases(object):
 
     def bind(self, rule, U, G, xi, switch=1.0, fixed_h=None):
         self.rule, self.U, self.G, self.xi, self.switch, self.fixed_h = rule, U, G, xi, switch, fixed_h
-        self.buf["cpp"] = torch.zeros(self.k, (self.k + 15) // 16 * 16, dtype=torch.float64)
+        ldk = (self.k + 15) // 16 * 16
+        self.buf["cpp"] = torch.zeros(self.k, ldk, dtype=torch.float64)
+        self.buf["p1"] = torch.zeros(self.p, ldk, dtype=torch.float64)
+        self.buf["gram_e"] = torch.zeros(self.k, ldk, dtype=torch.float64)
+        self.buf["gram_w"] = torch.zeros(self.k, ldk, dtype=torch.float64)
         return {"sums": self.sums, "centre": self.centre, "interact": self.interact, "drift": self.drift,
-                "update": self.update, "peek": self.peek, "cpp": self.cpp, "resolve": self.resolve}
+                "update": self.update, "peek": self.peek, "cpp": self.cpp, "resolve": self.resolve,
+                "products": self.products, "finish_factored": self.finish_factored}
 
     def sums(self):
         s = np.concatenate([self.G.sum(axis=1), self.U.sum(axis=1)])
@@ -84,6 +89,22 @@ class NumpyPhases(object):
         self.C = self.buf["cuu"].numpy()[:, :self.p].copy()
         if not skip:
             self.buf["scalars"][0, 0] = self._loops(self.W)
+
+    def products(self):
+        p, k, c = self.p, self.k, self.cols
+        self.C = self.buf["cuu"].numpy()[:, :p].copy()
+        E = self.buf["e_all"].numpy()[self.rank * k:(self.rank + 1) * k, :c]
+        Ut = self.buf["ut_all"].numpy()[self.rank * p:(self.rank + 1) * p, :c]
+        for name, val in (("p1", Ut @ E.T), ("gram_e", E @ E.T), ("gram_w", self.W @ self.W.T)):
+            b = self.buf[name].numpy()
+            b[:] = 0.0
+            b[:, :k] = val
+
+    def finish_factored(self):
+        k = self.k
+        self.V = (self.buf["p1"].numpy()[:, :k] @ self.W) / self.J
+        ssq = (self.buf["gram_e"].numpy()[:, :k] * self.buf["gram_w"].numpy()[:, :k]).sum() / self.J ** 2
+        self.buf["scalars"][0, 0] = ssq if self.rank == 0 else 0.0
 
     def peek(self):
         S = self.buf["scalars"][0].numpy()

@@ -93,6 +93,22 @@ def test_non_default_time_steps_match_oracle(d, k, J, dense):
             assert abs(s.metrics["t"][-1] - o["t"]) < TOL * o["t"], (rule, ts, t_hist)
 
 
+@pytest.mark.parametrize("d,k,J,dense", [(2, 10, 100, False), (40, 30, 17, True), (64, 50, 1024, False), (130, 257, 1000, True),
+                                         (1024, 10, 300, False)])
+def test_factored_formulation_matches_oracle(d, k, J, dense):
+    """formulation='factored' (D never formed) is the same update to rounding."""
+    pr = eo.linear_gaussian_problem(d, k, J, dense_gamma=dense)
+    for rule in RULES + ("eki",):
+        s = _sampler(d, k, J, pr["mu"], pr["Sigma0"], pr["ustar"])
+        o = eo.step(rule, pr["y"], pr["U0"], pr["G"], pr["Gamma"], pr["mu"], pr["Sigma0"], pr["ustar"], pr["xi"])
+        name = METHOD.get(rule, "eki_update")
+        Uk = getattr(s, name)(pr["y"], pr["U0"], pr["G"], pr["Gamma"], 0, xi=pr["xi"], formulation="factored")
+        assert _rel(Uk, o["Uk"]) < TOL, rule
+        assert abs(s.metrics["t"][-1] - o["hk"]) < TOL * o["hk"], rule
+        for key in ("self-bias", "bias", "self-bias-data", "bias-data"):
+            assert abs(s.metrics[key][-1] - o["metrics"][key]) <= TOL * abs(o["metrics"][key])
+
+
 def test_device_resident_step_with_strided_tensors():
     """Engine.step on CUDA tensors that are column slices of wider buffers (leading dimension != J, odd
     offset so the noise operand needs the internal re-pack)."""

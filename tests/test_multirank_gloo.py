@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 
-def _worker(rank, world, port, rule, d, k, J, q, ts=None, t_last=None):
+def _worker(rank, world, port, rule, d, k, J, q, ts=None, t_last=None, formulation="interaction"):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, HERE)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -35,7 +35,7 @@ def _worker(rank, world, port, rule, d, k, J, q, ts=None, t_last=None):
         elif ts == "mix":
             fixed, resolve = (0.02 if t_last >= 4.0 else None), (t_last, 1.0)
         phases = ph.bind(rule, pr["U0"][:, sl], pr["G"][:, sl], pr["xi"][:, sl], fixed_h=fixed)
-        run_phases(phases, ph.buffer, (dist, None, rank), d, k, rule, resolve)
+        run_phases(phases, ph.buffer, (dist, None, rank), d, k, rule, resolve, formulation)
         ref = eo.step(rule, pr["y"], pr["U0"], pr["G"], pr["Gamma"], pr["mu"], pr["Sigma0"], pr["ustar"], pr["xi"],
                       time_step=ts, delta_t=0.02, t_last=t_last)
         err = np.abs(ph.out - ref["Uk"][:, sl]).max() / np.abs(ref["Uk"]).max() if ph.cols else 0.0
@@ -50,12 +50,17 @@ def _worker(rank, world, port, rule, d, k, J, q, ts=None, t_last=None):
     (2, "aldi", 37, None, None), (2, "aldi_constant", 40, None, None), (2, "eks", 33, None, None),
     (3, "aldi", 16, None, None), (2, "eki", 21, None, None),
     (2, "aldi", 29, "constant", 0.3), (2, "eks", 26, "constant", None), (2, "aldi", 31, "mix", 1.5),
-    (2, "aldi", 31, "mix", 5.0)])
+    (2, "aldi", 31, "mix", 5.0), (2, "aldi", 35, "factored", None), (3, "eks", 22, "factored", None),
+    (2, "aldi_constant", 27, "factored", None)])
 def test_sharded_orchestration_matches_single_process(world, rule, J, ts, t_last):
+    formulation = "interaction"
+    if ts == "factored":
+        ts, formulation = None, "factored"
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29500 + (os.getpid() + J + len(str(ts)) * 7 + int((t_last or 0) * 10)) % 2000
-    procs = [ctx.Process(target=_worker, args=(r, world, port, rule, 5, 7, J, q, ts, t_last)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, rule, 5, 7, J, q, ts, t_last, formulation))
+             for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
