@@ -15,6 +15,7 @@ CES_OK = 0
 CES_ERR_INVALID, CES_ERR_STATE, CES_ERR_ALIGN, CES_ERR_NOT_SPD, CES_ERR_CUDA, CES_ERR_NOMEM = -1, -2, -3, -4, -5, -6
 RULES = {"eks": 0, "aldi": 1, "aldi_constant": 2, "eki": 3}
 TS_FROBENIUS, TS_FIXED, TS_KEEP = 0, 1, 2
+FORMULATIONS = {"interaction": 0, "factored": 1}
 MAPS = {"lineal": 0, "lineal_log": 1, "elliptic": 2, "banana": 3}
 
 # every symbol include/ces_b200.h declares (tests/test_abi.py checks the .so exports them all)
@@ -66,9 +67,9 @@ def load():
     lib.ces_phase4a_drift.argtypes = [_vp, _dbl]
     lib.ces_phase4_update.argtypes = [_vp, _int, _int, _dbl, _dp, _i64, _dp, _i64, _dp, _i64,
                                       ctypes.POINTER(_dbl), ctypes.POINTER(_dbl)]
-    lib.ces_step.argtypes = [_vp, _int, _int, _dbl, _dbl, _dp, _i64, _dp, _i64, _dp, _i64, _dp, _i64,
+    lib.ces_step.argtypes = [_vp, _int, _int, _dbl, _dbl, _int, _dp, _i64, _dp, _i64, _dp, _i64, _dp, _i64,
                              ctypes.POINTER(_dbl), ctypes.POINTER(_dbl)]
-    lib.ces_step_host.argtypes = [_vp, _int, _int, _dbl, _dbl, _dp, _dp, _dp, _dp,
+    lib.ces_step_host.argtypes = [_vp, _int, _int, _dbl, _dbl, _int, _dp, _dp, _dp, _dp,
                                   ctypes.POINTER(_dbl), ctypes.POINTER(_dbl)]
     lib.ces_forward_map.argtypes = [_vp, _int, _dp, _i64, _dp, _dp, _dp, _i64, _dp, _i64]
     lib.ces_buffer.argtypes = [_vp, ctypes.c_char_p, ctypes.POINTER(_vp), ctypes.POINTER(_i64),

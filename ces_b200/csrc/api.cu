@@ -684,20 +684,29 @@ int ces_phase4_update(ces_handle_t h, int rule, int ts_kind, double fixed_h, con
     return CES_OK;
 }
 
-int ces_step(ces_handle_t h, int rule, int ts_kind, double fixed_h, double switch_, const double* U, int64_t ldu,
-             const double* G, int64_t ldg, const double* xi, int64_t ldxi, double* Uout, int64_t ldo, double* hk_host,
-             double* metrics_host) {
+static int interaction_phase(ces_handle_t h, int rule, int formulation) {
+    if (formulation == CES_FORM_FACTORED) {
+        CES_TRY(ces_phase3f_products(h, rule));
+        return ces_phase3f_finish(h, rule);
+    }
+    if (formulation != CES_FORM_INTERACTION) return fail(CES_ERR_INVALID, "unknown formulation%s", "");
+    return ces_phase3_interact(h, rule, 0);
+}
+
+int ces_step(ces_handle_t h, int rule, int ts_kind, double fixed_h, double switch_, int formulation, const double* U,
+             int64_t ldu, const double* G, int64_t ldg, const double* xi, int64_t ldxi, double* Uout, int64_t ldo,
+             double* hk_host, double* metrics_host) {
     CES_TRY(valid(h, true));
     if (h->nranks != 1) return fail(CES_ERR_STATE, "ces_step is single-GPU; use the phases with nranks > 1%s", "");
     CES_TRY(ces_phase1_sums(h, U, ldu, G, ldg));
     CES_TRY(ces_phase2_centre(h, rule, U, ldu, G, ldg));
-    CES_TRY(ces_phase3_interact(h, rule, 0));
+    CES_TRY(interaction_phase(h, rule, formulation));
     if (rule == CES_RULE_ALDI_CONSTANT) CES_TRY(ces_phase4a_drift(h, switch_));
     return ces_phase4_update(h, rule, ts_kind, fixed_h, U, ldu, xi, ldxi, Uout, ldo, hk_host, metrics_host);
 }
 
-int ces_step_host(ces_handle_t h, int rule, int ts_kind, double fixed_h, double switch_, const double* U, const double* G,
-                  const double* xi, double* Uout, double* hk_host, double* metrics_host) {
+int ces_step_host(ces_handle_t h, int rule, int ts_kind, double fixed_h, double switch_, int formulation, const double* U,
+                  const double* G, const double* xi, double* Uout, double* hk_host, double* metrics_host) {
     CES_TRY(valid(h, true));
     if (h->nranks != 1) return fail(CES_ERR_STATE, "ces_step_host is single-GPU%s", "");
     if (!U || !G || !Uout) return fail(CES_ERR_INVALID, "ces_step_host: null pointer%s", "");
@@ -730,7 +739,7 @@ int ces_step_host(ces_handle_t h, int rule, int ts_kind, double fixed_h, double 
     CES_CUDA(h2d(h->stage_G, G, k, h->st));
     CES_TRY(ces_phase1_sums(h, h->stage_U, ld, h->stage_G, ld));
     CES_TRY(ces_phase2_centre(h, rule, h->stage_U, ld, h->stage_G, ld));
-    CES_TRY(ces_phase3_interact(h, rule, 0));
+    CES_TRY(interaction_phase(h, rule, formulation));
     if (rule == CES_RULE_ALDI_CONSTANT) CES_TRY(ces_phase4a_drift(h, switch_));
     if (xi) CES_CUDA(cudaStreamWaitEvent(h->st, h->copy_ev, 0));
     // phase 4 ends with a stream synchronisation (status + scalars); queue the result copy before it

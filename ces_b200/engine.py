@@ -225,9 +225,9 @@ class Engine(object):
         lib, h = self.lib, self.h
         if formulation not in ("interaction", "factored"):
             raise ValueError("formulation must be 'interaction' or 'factored'")
-        if self.nranks == 1 and resolve is None and formulation == "interaction":
-            _lib.check(lib.ces_step(h, r, ts, fh, float(switch), Up, ldu, Gp, ldg, Xp, ldx, Op, ldo,
-                                    ctypes.byref(self._hk), self._met))
+        if self.nranks == 1 and resolve is None:
+            _lib.check(lib.ces_step(h, r, ts, fh, float(switch), _lib.FORMULATIONS[formulation], Up, ldu, Gp, ldg, Xp, ldx,
+                                    Op, ldo, ctypes.byref(self._hk), self._met))
         else:
             def peek():
                 hk = ctypes.c_double()
@@ -257,8 +257,10 @@ class Engine(object):
         of the call.  This is what ``sampling.eks_update*`` invoke."""
         if self.nranks != 1:
             raise RuntimeError("step_host is single-GPU; shard device tensors and call step()")
-        if resolve is not None or formulation != "interaction":
-            # non-default time_step / formulation: the phase-by-phase device path, with explicit copies around it
+        if formulation not in _lib.FORMULATIONS:
+            raise ValueError("formulation must be 'interaction' or 'factored'")
+        if resolve is not None:
+            # non-default time_step: the phase-by-phase device path, with explicit copies around it
             torch = self.torch
             dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
             out, hk, met = self.step(rule, dev(U), dev(G), dev(xi) if xi is not None else None, fixed_h=fixed_h,
@@ -279,7 +281,8 @@ class Engine(object):
             xp = _lib.host_ptr(xi)
         else:
             xp = None
-        _lib.check(self.lib.ces_step_host(self.h, r, ts, fh, float(switch), _lib.host_ptr(U), _lib.host_ptr(G), xp,
+        _lib.check(self.lib.ces_step_host(self.h, r, ts, fh, float(switch), _lib.FORMULATIONS[formulation],
+                                          _lib.host_ptr(U), _lib.host_ptr(G), xp,
                                           _lib.host_ptr(out), ctypes.byref(self._hk), self._met))
         met = {key: float(self._met[i]) for i, key in enumerate(_METRIC_KEYS)}
         return out, float(self._hk.value), met

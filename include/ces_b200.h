@@ -50,6 +50,10 @@ extern "C" {
 #define CES_TS_FIXED 1            /* h given by the caller ('constant', and 'mix' after spin-up)     */
 #define CES_TS_KEEP 2             /* phase 4 keeps the h fixed earlier by ces_peek_step_size          */
 
+/* formulation of the interaction term */
+#define CES_FORM_INTERACTION 0    /* D = (1/J) E^T W formed in panels, V = U~ D (the reference's formulation) */
+#define CES_FORM_FACTORED 1       /* V = (1/J)(U~ E^T) W, ||D||_F from Gram matrices; same update to rounding */
+
 /* forward maps (ces/utils.py) */
 #define CES_MAP_LINEAL 0          /* A theta + b           :25-31  */
 #define CES_MAP_LINEAL_LOG 1      /* A exp(phi) + b        :39-42  */
@@ -116,15 +120,15 @@ int ces_phase4_update(ces_handle_t h, int rule, int ts_kind, double fixed_h, con
                       double* metrics_host /* [4] */);
 
 /* One whole single-GPU step on device buffers (nranks must be 1). */
-int ces_step(ces_handle_t h, int rule, int ts_kind, double fixed_h, double switch_, const double* U_dev, int64_t ldu,
-             const double* G_dev, int64_t ldg, const double* xi_dev, int64_t ldxi, double* Uout_dev, int64_t ldo,
-             double* hk_host, double* metrics_host);
+int ces_step(ces_handle_t h, int rule, int ts_kind, double fixed_h, double switch_, int formulation,
+             const double* U_dev, int64_t ldu, const double* G_dev, int64_t ldg, const double* xi_dev, int64_t ldxi,
+             double* Uout_dev, int64_t ldo, double* hk_host, double* metrics_host);
 
 /* The same step on HOST buffers (dense, ld = J): host->device copies of U, G, xi and the device->host
  * copy of U_out happen inside the call.  This is the call behind sampling.eks_update*(numpy arrays). */
-int ces_step_host(ces_handle_t h, int rule, int ts_kind, double fixed_h, double switch_, const double* U_host,
-                  const double* G_host, const double* xi_host, double* Uout_host, double* hk_host,
-                  double* metrics_host);
+int ces_step_host(ces_handle_t h, int rule, int ts_kind, double fixed_h, double switch_, int formulation,
+                  const double* U_host, const double* G_host, const double* xi_host, double* Uout_host,
+                  double* hk_host, double* metrics_host);
 
 /* Batched forward map G[:, j] = model(U[:, j]) for this rank's columns (enka.G_ens, ces/calibrate.py:106-130).
  * CES_MAP_LINEAL / _LOG: A_dev is k x p (ld = lda, even, 16-byte aligned), b_dev is k doubles or NULL.
