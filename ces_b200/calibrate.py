@@ -15,12 +15,18 @@ ces/calibrate.py:404-416).  What differs is where the arithmetic runs:
   for the whole ensemble on the device; any other ``model.type == 'map'`` callable is
   evaluated particle by particle on the host exactly as ``enka.G_ens`` does
   (ces/calibrate.py:106-130) -- that is the user's model, not a fallback of ours.
+* ``model.type == 'pde'`` models (ODE integrators + statistics, ces/calibrate.py:132-168) keep the reference's host
+  protocol for the forward pass (``G_pde_ens``: the user's ``model.solve`` / ``model.statistics`` per particle, joblib
+  when ``self.parallel``) with the state carry-over ``W0`` / ``ws`` / ``wt`` / ``update_wt`` semantics of ``run``; the
+  update still runs on the device.
 * Noise: by default ``xi = np.random.normal(0, 1, [p, J])`` is drawn from the global
   numpy RNG at the point where the reference draws it (ces/calibrate.py:447,488,527),
   so a seeded script consumes the same random stream.
 * ``formulation='factored'`` (kwarg of ``run`` / ``eks_update*`` or attribute; default ``'interaction'``) computes
   the same update without forming the J x J matrix D: ``(U - ubar) D = (1/J) ((U - ubar) E^T) W`` and ``||D||_F`` from
   two k x k Gram matrices -- identical to rounding (~1e-15), ``O(d k J + k^2 J)`` instead of ``O((k + d) J^2)``.
+* ``rng='device'`` (kwarg of ``run`` or attribute, with ``seed``) generates the noise on the GPU (Philox + Box-Muller,
+  ``ces_fill_normal``) instead of drawing it with numpy on the host: a different but equally distributed stream.
 * Multi-GPU: if ``self.group`` is a ``torch.distributed`` process group, every rank
   calls ``run`` with the same arguments and the ensemble is sharded by particle
   columns.
@@ -136,6 +142,27 @@ class enka(object):
         out = np.zeros((self.n_obs, theta.shape[1]))
         for j, col in enumerate(theta.T):
             out[:, j] = model(col)
+        return out
+
+    def G_pde(self, k, model, t):
+        """One particle of an ODE/PDE-constrained model (ces/calibrate.py:132-154): ``k`` stacks the p parameters
+        and the n_state initial condition; returns the statistics followed by the final state."""
+        w0 = k[self.p:]
+        ws = model.solve(w0, t, args=tuple(k[:self.p]))
+        gs = model.statistics(ws)
+        return np.concatenate([gs, ws[-1]])
+
+    def G_pde_ens(self, theta, model, t):
+        """``G_pde`` for every column of theta (ces/calibrate.py:156-168).  The integrators of these models are the
+        user's (scipy) code and run on the host, one particle at a time or through joblib like the reference."""
+        if self.parallel:
+            from joblib import Parallel, delayed
+
+            cols = Parallel(n_jobs=self.num_cores)(delayed(self.G_pde)(col, model, t) for col in theta.T)
+            return np.asarray(cols).T
+        out = np.zeros((self.n_obs + model.n_state, theta.shape[1]))
+        for j, col in enumerate(theta.T):
+            out[:, j] = self.G_pde(col, model, t)
         return out
 
     @staticmethod
@@ -334,11 +361,9 @@ class sampling(enka):
             self.directory = os.getcwd()
         rule = kwargs.get('update', 'aldi')
         self._update_name = rule
-        if mtype == 'pde':
-            raise NotImplementedError("'pde'-type forward models (ces/calibrate.py:132-168) are outside the "
-                                      "accelerated path this round (SURVEY.md section 8f rank 2)")
-        if mtype != 'map':
+        if mtype not in ('map', 'pde'):
             raise ValueError("model.type must be 'map' or 'pde'")
+        is_pde = (mtype == 'pde')
         self._ensure_metrics()
         self._step_options(rule, kwargs)            # validates time_step before any work
         group = getattr(self, 'group', None)
@@ -356,11 +381,42 @@ class sampling(enka):
         self._ensure_metrics()
 
         U_dev = torch.from_numpy(U0[:, lo:hi].copy()).to(dev)
-        device_model = self._is_device_model(model)
+        device_model = (not is_pde) and self._is_device_model(model)
+        if is_pde:
+            # initial conditions of the integrator, one per particle (ces/calibrate.py:317-327)
+            t_ode, ws_pool = kwargs.get('t', None), kwargs.get('ws', None)
+            if ws_pool is not None:
+                widx = np.random.randint(ws_pool.shape[0], size=self.J)
+                self.W0 = ws_pool[widx].T
+                self.Wall = [widx]
+            else:
+                self.W0 = np.tile(kwargs.get('wt', None), self.J).reshape(self.J, model.n_state).T
         G_dev = torch.empty(self.n_obs, hi - lo, dtype=torch.float64, device=dev)
         known = rule in _RULE_METHOD
 
-        def forward(U_dev):
+        def forward_pde(U_dev, final):
+            """Statistics + carried-over state (ces/calibrate.py:342-350, 390-396): the user's integrator on the host for
+            this rank's particles; the full (n_obs + n_state, J) array is needed on every rank for the next W0."""
+            U_loc = U_dev.cpu().numpy()
+            G_loc = self.G_pde_ens(np.vstack([U_loc, self.W0[:, lo:hi]]), model, t_ode)
+            if eng.nranks > 1:
+                G_full = gather_host(torch.from_numpy(np.ascontiguousarray(G_loc)).to(dev), G_loc.shape[0])
+            else:
+                G_full = G_loc
+            if kwargs.get('update_wt', True):
+                if ws_pool is not None:
+                    widx = np.random.randint(ws_pool.shape[0], size=self.J)
+                    if not final:
+                        self.Wall.append(widx)
+                    self.W0 = ws_pool[widx].T
+                else:
+                    self.W0 = np.copy(G_full[self.n_obs:, :])
+            G_dev.copy_(torch.from_numpy(np.ascontiguousarray(G_full[:self.n_obs, lo:hi])))
+            return G_dev, G_full
+
+        def forward(U_dev, final=False):
+            if is_pde:
+                return forward_pde(U_dev, final)
             if device_model:
                 model.evaluate_ensemble(eng, U_dev, G_dev)
                 return G_dev, None
@@ -383,14 +439,20 @@ class sampling(enka):
             G_cur, G_host = forward(U_dev)
             if trace:
                 self.Uall.append(gather_host(U_dev, self.p))
-                self.Gall.append(G_host if (G_host is not None and eng.nranks == 1) else gather_host(G_cur, self.n_obs))
+                self.Gall.append(G_host if (G_host is not None and (eng.nranks == 1 or is_pde))
+                                 else gather_host(G_cur, self.n_obs))
             if known:
                 setattr(self, 'update_rule', {'eks': 'eks_update', 'aldi': 'eks_update_linear',
                                               'aldi_constant': 'eks_update_aldi', 'eki': 'eki_update'}[rule])
                 xi_dev = None
                 if rule != 'eki':
-                    xi = self._draw_noise((self.p, J), kwargs)          # same stream on every rank
-                    xi_dev = torch.from_numpy(np.ascontiguousarray(xi[:, lo:hi])).to(dev)
+                    if kwargs.get('rng', getattr(self, 'rng', 'numpy')) == 'device':
+                        # production mode: Philox noise generated on the device, nothing crosses PCIe
+                        xi_dev = eng.normal_noise(self.p, kwargs.get('seed', getattr(self, 'seed', 0)),
+                                                  len(self.metrics['t']))
+                    else:
+                        xi = self._draw_noise((self.p, J), kwargs)      # same stream on every rank
+                        xi_dev = torch.from_numpy(np.ascontiguousarray(xi[:, lo:hi])).to(dev)
                 fixed, resolve = self._step_options(rule, kwargs)     # 'mix' depends on the time reached so far
                 U_dev, hk, met = eng.step(rule, U_dev, G_cur, xi_dev, fixed_h=fixed, switch=kwargs.get('switch', 1.),
                                           resolve=resolve,
@@ -407,9 +469,9 @@ class sampling(enka):
             if self.metrics['t'][-1] > kwargs.get('t_tol', 2.):
                 break
 
-        G_cur, G_host = forward(U_dev)
+        G_cur, G_host = forward(U_dev, final=True)
         U_fin = gather_host(U_dev, self.p)
-        G_fin = G_host if (G_host is not None and eng.nranks == 1) else gather_host(G_cur, self.n_obs)
+        G_fin = G_host if (G_host is not None and (eng.nranks == 1 or is_pde)) else gather_host(G_cur, self.n_obs)
         if trace:
             self.Uall.append(U_fin)
             self.Gall.append(G_fin)

@@ -839,6 +839,12 @@ int ces_buffer(ces_handle_t h, const char* name, double** ptr, int64_t* rows, in
     return CES_OK;
 }
 
+int ces_fill_normal(void* stream, uint64_t seed, uint64_t step, double* X, int64_t ld, int64_t rows, int64_t cols,
+                    int64_t col_offset) {
+    if (!X || ld < cols) return fail(CES_ERR_INVALID, "ces_fill_normal: bad argument%s", "");
+    return fill_normal(static_cast<cudaStream_t>(stream), X, ld, rows, cols, col_offset, seed, step);
+}
+
 int ces_gemm(void* stream, int a_mode, int b_mode, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
              const double* B, int64_t ldb, double beta, double* C, int64_t ldc) {
     if (a_mode < 0 || a_mode > 1 || b_mode < 0 || b_mode > 1 || M > (1ll << 30) || N > (1ll << 30) || K > (1ll << 30))

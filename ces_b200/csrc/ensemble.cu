@@ -396,6 +396,52 @@ int add_col_vector(cudaStream_t st, double* X, int64_t ld, int64_t rows, int64_t
     return CES_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Standard normal noise generated on the device (production alternative to the host numpy draw of
+// ces/calibrate.py:447,488,527): Philox4x32-10 keyed by the seed, counter = (global element pair, step), two
+// 53-bit uniforms per call turned into two normals by Box-Muller.  The value of element (row, global column)
+// depends only on (seed, step, row, column), so a column-sharded ensemble draws what a single GPU would.
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+__global__ void __launch_bounds__(256) fill_normal_kernel(double* __restrict__ X, long long ld, int rows, long long cols,
+                                                          long long col_offset, unsigned long long seed,
+                                                          unsigned long long step) {
+    const long long pair = (long long)blockIdx.x * 256 + threadIdx.x;      // local column pair
+    const int row = blockIdx.y;
+    const long long j = 2 * pair;
+    if (j >= cols) return;
+    const unsigned long long gpair = (unsigned long long)(col_offset + j) >> 1;   // col_offset is even
+    uint32_t c[4] = {(uint32_t)gpair, (uint32_t)(gpair >> 32), (uint32_t)row, (uint32_t)step};
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        philox_round(c, k0, k1);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    const double two53 = 1.0 / 9007199254740992.0;
+    const double u1 = ((double)((((unsigned long long)c[0] << 32) | c[1]) >> 11) + 0.5) * two53;   // (0, 1)
+    const double u2 = ((double)((((unsigned long long)c[2] << 32) | c[3]) >> 11) + 0.5) * two53;
+    const double rad = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    X[(size_t)row * ld + j] = rad * cs;
+    if (j + 1 < cols) X[(size_t)row * ld + j + 1] = rad * sn;
+}
+int fill_normal(cudaStream_t st, double* X, int64_t ld, int64_t rows, int64_t cols, int64_t col_offset, uint64_t seed,
+                uint64_t step) {
+    if (rows < 1 || cols < 1) return CES_OK;
+    if (col_offset & 1) return fail(CES_ERR_INVALID, "fill_normal: column offset must be even%s", "");
+    dim3 grid((unsigned)ceil_div(ceil_div(cols, 2), 256), (unsigned)rows);
+    fill_normal_kernel<<<grid, 256, 0, st>>>(X, ld, (int)rows, cols, col_offset, seed, step);
+    CES_LAUNCHED(1);
+    return CES_OK;
+}
+
 // M = Sigma0 + (*h) * C  (dense, p x p) or diag(sig) + (*h) * C.
 __global__ void __launch_bounds__(256) form_implicit_kernel(const double* __restrict__ C, long long ldc,
                                                             const double* __restrict__ Sigma0, long long lds,

@@ -75,6 +75,8 @@ int pad_copy(cudaStream_t st, const double* X, int64_t ldx, int64_t rows, int64_
 int row_scale(cudaStream_t st, const double* diag, double* X, int64_t ld, int64_t rows, int64_t cols);
 int add_col_vector(cudaStream_t st, double* X, int64_t ld, int64_t rows, int64_t cols, const double* v, double s,
                    const double* s_dev);
+int fill_normal(cudaStream_t st, double* X, int64_t ld, int64_t rows, int64_t cols, int64_t col_offset, uint64_t seed,
+                uint64_t step);
 int form_implicit(cudaStream_t st, const double* C, int64_t ldc, const double* Sigma0, int64_t lds,
                   const double* sig_diag, const double* h_dev, int64_t p, double* M, int64_t ldm);
 

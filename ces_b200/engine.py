@@ -195,6 +195,20 @@ class Engine(object):
         _lib.check(self.lib.ces_profile_read(self.h, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(fl)))
         return ms.value, n.value, fl.value
 
+    def normal_noise(self, rows, seed, step, out=None):
+        """(rows, cols) standard normal noise for this rank's columns, generated on the device (ces_fill_normal);
+        identical to the corresponding columns of a single-GPU draw with the same (seed, step)."""
+        torch = self.torch
+        if self.col_lo % 2:
+            raise ValueError("device noise needs an even shard offset (use an even shard width)")
+        if out is None:
+            out = torch.empty(rows, self.cols, dtype=torch.float64, device="cuda")
+        if self.cols:
+            _lib.check(self.lib.ces_fill_normal(ctypes.c_void_p(self.stream.cuda_stream), int(seed), int(step),
+                                                ctypes.c_void_p(out.data_ptr()), int(out.stride(0)), int(rows),
+                                                int(self.cols), int(self.col_lo)))
+        return out
+
     def launch_count(self):
         return int(self.lib.ces_launch_count(self.h))
 

@@ -92,3 +92,26 @@ def test_cholesky_reports_the_failing_pivot():
     assert s == _lib.CES_ERR_NOT_SPD and b"pivot 71" in lib.ces_last_error()
     with pytest.raises(np.linalg.LinAlgError):
         _lib.check(s)
+
+
+def test_device_normal_noise_is_standard_normal_and_shard_invariant():
+    """ces_fill_normal: moments of N(0,1), reproducible by (seed, step), different across steps, and a column shard
+    draws exactly the columns a single GPU would."""
+    from ces_b200.engine import Engine
+
+    eng = Engine(8, 4, 200000)
+    try:
+        a = eng.normal_noise(8, seed=7, step=3)
+        b = eng.normal_noise(8, seed=7, step=3)
+        c = eng.normal_noise(8, seed=7, step=4)
+        assert torch.equal(a, b) and not torch.equal(a, c)
+        x = a.flatten()
+        assert abs(float(x.mean())) < 5e-3 and abs(float(x.var()) - 1.0) < 1e-2
+        assert abs(float((x ** 3).mean())) < 2e-2 and abs(float((x ** 4).mean()) - 3.0) < 5e-2
+        assert abs(float((a[0] * a[1]).mean())) < 1e-2 and abs(float((a[0, :-1] * a[0, 1:]).mean())) < 1e-2
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        part = torch.empty(8, 1000, dtype=torch.float64, device="cuda")
+        _lib.check(eng.lib.ces_fill_normal(st, 7, 3, ctypes.c_void_p(part.data_ptr()), part.stride(0), 8, 1000, 5000))
+        assert torch.equal(part, a[:, 5000:6000])
+    finally:
+        eng.close()

@@ -288,3 +288,61 @@ def test_full_size_permutation_equivariance(cfg3):
                                  c["xi"][:, perm].contiguous())
     assert abs(hk2 - c["hk"]) < 1e-11 * c["hk"]
     assert float((out2 - c["out"][:, perm]).abs().max() / c["out"].abs().max()) < TOL
+
+
+class _DampedOscillator(object):
+    """A 'pde'-type model in the reference's protocol (ces/utils.py:124-194 is the Lorenz-63 instance of it):
+    solve(w0, t, args) integrates an ODE, statistics(ws) reduces the trajectory, n_state is the carried state."""
+    type = "pde"
+    model_name = "oscillator"
+    n_state = 2
+    n_obs = 3
+
+    def solve(self, w0, t, args=()):
+        k, c = args
+        ws = np.empty((len(t), 2))
+        ws[0] = w0
+        for n in range(1, len(t)):
+            h = t[n] - t[n - 1]
+            x, v = ws[n - 1]
+            ws[n] = [x + h * v, v + h * (-np.exp(k) * x - np.exp(c) * v + 1.0)]
+        return ws
+
+    def statistics(self, ws):
+        return np.array([ws[:, 0].mean(), ws[:, 1].mean(), (ws[:, 0] ** 2).mean()])
+
+
+@pytest.mark.parametrize("use_pool", [False, True])
+def test_run_with_a_pde_type_model(use_pool):
+    """'pde' branch of sampling.run (ces/calibrate.py:317-327, 342-350, 390-396): state carry-over W0, the ws pool
+    with its np.random.randint draws interleaved with the noise draws, Gall holding statistics + final state."""
+    model, J, T, p = _DampedOscillator(), 30, 4, 2
+    rng = np.random.default_rng(0)
+    U0 = 0.3 * rng.standard_normal((p, J))
+    y, Gamma = np.array([0.4, 0.0, 0.3]), 0.01 * np.eye(3)
+    t = np.linspace(0.0, 2.0, 41)
+    wt = np.array([0.5, 0.0])
+    pool = rng.standard_normal((17, 2)) if use_pool else None
+    s = calibrate.sampling(p, 3, J)
+    s.ustar, s.mu, s.sigma, s.T = np.zeros((p, 1)), np.zeros((p, 1)), 4.0 * np.eye(p), T
+    np.random.seed(21)
+    s.run(y, U0, model, Gamma, None, wt=wt, t=t, ws=pool, t_tol=1e9)
+    # the reference protocol, stepped with the oracle
+    np.random.seed(21)
+    e = calibrate.enka(p, 3, J)
+    if pool is not None:
+        W0 = pool[np.random.randint(pool.shape[0], size=J)].T
+    else:
+        W0 = np.tile(wt, J).reshape(J, 2).T
+    U, tt = U0, None
+    for _ in range(T):
+        G = e.G_pde_ens(np.vstack([U, W0]), model, t)
+        W0 = pool[np.random.randint(pool.shape[0], size=J)].T if pool is not None else np.copy(G[3:, :])
+        o = eo.step("aldi", y, U, G[:3], Gamma, s.mu, s.sigma, s.ustar, np.random.normal(0, 1, [p, J]), t_last=tt)
+        U, tt = o["Uk"], o["t"]
+    G = e.G_pde_ens(np.vstack([U, W0]), model, t)
+    assert _rel(s.Ustar, U) < 1e-8
+    assert s.Gall.shape == (T + 1, 3 + 2, J) and _rel(s.Gall[-1], G) < 1e-8
+    assert _rel(s.Gstar, G[:3]) < 1e-8
+    if pool is not None:
+        assert len(s.Wall) == T + 1
