@@ -164,6 +164,12 @@ int ces_darcy_destroy(void* model);
 int ces_darcy_forward(void* model, const double* U_dev, int64_t ldu, int64_t cols, double* G_dev, int64_t ldg,
                       int full_solution, double tol, int max_iter, int* iters_host);
 
+/* N(0,1) noise on the device (production alternative to the host draw np.random.normal(0,1,[p,J]) of
+ * ces/calibrate.py:447,488,527): Philox4x32-10 + Box-Muller.  Element (row, col_offset + col) depends only on
+ * (seed, step, row, global column), so a column-sharded ensemble draws exactly what one GPU would (col_offset even). */
+int ces_fill_normal(void* stream, uint64_t seed, uint64_t step, double* X_dev, int64_t ld, int64_t rows, int64_t cols,
+                    int64_t col_offset);
+
 /* ---- building blocks exported for tests and for callers that own their orchestration ---------------
  * C[M,N] = alpha * op(A) op(B) + beta * C on the FP64 tensor cores.  a_mode: 0 = A is M x K row-major,
  * 1 = A is stored K x M (i.e. A^T given); b_mode: 0 = B is K x N row-major, 1 = B stored N x K.
