@@ -39,6 +39,7 @@ WORKLOADS = {
     "target": (1024, 4096, 65536, 2048),     # BASELINE.json "Target": one EKS step at J=65536, d=1024, k=4096
     "cfg3": (1024, 4096, 16384, 2048),       # BASELINE.json configs[2]
     "small": (64, 50, 1024, 1024),           # configs[1] shape (smoke-sized)
+    "cfg1": (2, 10, 100, 100),               # configs[0]: the reference's own CPU-runnable case
 }
 METRIC = "particle-updates/sec (J*steps/s) for one EKS step"
 NOMINAL_FP64_TFLOPS = 148 * 128 * 1.965e9 / 1e12
