@@ -14,6 +14,7 @@ struct ces_handle_s {
     int64_t ldJ = 0, ldp = 0, ldk = 0, ldD = 0, panel = 0;
     cudaStream_t st = nullptr;
     bool have_problem = false, gamma_diag = true, sigma_diag = true;
+    bool use_small = true;              // single-kernel path for small problems (CES_NO_SMALL_PATH=1 disables it)
     int last_rule = -1;
     // problem data (device)
     double *y = nullptr, *ginv_diag = nullptr, *Ginv = nullptr, *mu = nullptr, *ustar = nullptr;
@@ -147,6 +148,7 @@ int ces_create(int64_t p, int64_t k, int64_t J_local, int64_t J_global, int rank
     h->p = p; h->k = k; h->Jl = J_local; h->Jg = J_global; h->cols = cols_local;
     h->rank = rank; h->nranks = nranks;
     h->st = static_cast<cudaStream_t>(stream);
+    h->use_small = std::getenv("CES_NO_SMALL_PATH") == nullptr;
     h->ldJ = padded_ld(J_local);
     h->ldp = padded_ld(p);
     h->ldk = padded_ld(k);
@@ -698,6 +700,36 @@ int ces_step(ces_handle_t h, int rule, int ts_kind, double fixed_h, double switc
              double* hk_host, double* metrics_host) {
     CES_TRY(valid(h, true));
     if (h->nranks != 1) return fail(CES_ERR_STATE, "ces_step is single-GPU; use the phases with nranks > 1%s", "");
+    if (h->use_small && formulation == CES_FORM_INTERACTION && small_step_eligible(h->p, h->k, h->Jl)) {
+        // small problems: the whole update in one single-CTA kernel (launch latency dominates otherwise)
+        if (rule < CES_RULE_EKS || rule > CES_RULE_EKI) return fail(CES_ERR_INVALID, "unknown update rule %s%lld", "", rule);
+        if (ts_kind != CES_TS_FROBENIUS && ts_kind != CES_TS_FIXED) return fail(CES_ERR_INVALID, "unknown step-size rule%s", "");
+        if (!U || !G || !Uout || (rule != CES_RULE_EKI && !xi)) return fail(CES_ERR_INVALID, "ces_step: null pointer%s", "");
+        SmallStepCall c;
+        c.p = h->p; c.k = h->k; c.J = h->Jl; c.rule = rule; c.ts_kind = ts_kind; c.fixed_h = fixed_h; c.switch_ = switch_;
+        c.U = U; c.G = G; c.xi = xi; c.ldu = ldu; c.ldg = ldg; c.ldxi = ldxi; c.out = Uout; c.ldo = ldo;
+        c.y = h->y; c.mu = h->mu; c.ustar = h->ustar; c.bprior = h->bprior;
+        c.ginv_diag = h->gamma_diag ? h->ginv_diag : nullptr; c.Ginv = h->gamma_diag ? nullptr : h->Ginv;
+        c.sinv_diag = h->sinv_diag; c.sig_diag = h->sig_diag;
+        c.Sinv = h->sigma_diag ? nullptr : h->Sinv; c.Sigma0 = h->sigma_diag ? nullptr : h->Sigma0;
+        c.ldk = h->ldk; c.ldp = h->ldp; c.S = h->S; c.info = h->info;
+        h->last_rule = rule;
+        CES_TRY(small_step(h->st, c));
+        CES_CUDA(cudaMemcpyAsync(h->hS, h->S, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+        if (h->pending_out) {
+            const size_t wbytes = h->Jl * sizeof(double);
+            if (ldo == h->Jl) CES_CUDA(cudaMemcpyAsync(h->pending_out, Uout, (size_t)h->pending_rows * wbytes, cudaMemcpyDeviceToHost, h->st));
+            else CES_CUDA(cudaMemcpy2DAsync(h->pending_out, wbytes, Uout, ldo * sizeof(double), wbytes, h->pending_rows, cudaMemcpyDeviceToHost, h->st));
+        }
+        CES_TRY(check_info(h, "cov(U)"));
+        if (hk_host) *hk_host = h->hS[S_H];
+        if (metrics_host) {
+            const double J = (double)h->Jg;
+            metrics_host[0] = h->hS[S_SELF_BIAS] / J; metrics_host[1] = h->hS[S_BIAS] / J;
+            metrics_host[2] = h->hS[S_SELF_DATA] / J; metrics_host[3] = h->hS[S_BIAS_DATA] / J;
+        }
+        return CES_OK;
+    }
     CES_TRY(ces_phase1_sums(h, U, ldu, G, ldg));
     CES_TRY(ces_phase2_centre(h, rule, U, ldu, G, ldg));
     CES_TRY(interaction_phase(h, rule, formulation));
@@ -737,6 +769,15 @@ int ces_step_host(ces_handle_t h, int rule, int ts_kind, double fixed_h, double 
     }
     CES_CUDA(h2d(h->stage_U, U, p, h->st));
     CES_CUDA(h2d(h->stage_G, G, k, h->st));
+    if (h->use_small && formulation == CES_FORM_INTERACTION && small_step_eligible(h->p, h->k, h->Jl)) {
+        if (xi) CES_CUDA(cudaStreamWaitEvent(h->st, h->copy_ev, 0));
+        h->pending_out = Uout;
+        h->pending_rows = p;
+        const int s1 = ces_step(h, rule, ts_kind, fixed_h, switch_, formulation, h->stage_U, ld, h->stage_G, ld,
+                                xi ? h->stage_xi : nullptr, ld, h->stage_out, ld, hk_host, metrics_host);
+        h->pending_out = nullptr;
+        return s1;
+    }
     CES_TRY(ces_phase1_sums(h, h->stage_U, ld, h->stage_G, ld));
     CES_TRY(ces_phase2_centre(h, rule, h->stage_U, ld, h->stage_G, ld));
     CES_TRY(interaction_phase(h, rule, formulation));

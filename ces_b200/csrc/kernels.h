@@ -95,6 +95,24 @@ int spd_inverse_from_factor(cudaStream_t st, const double* L, int64_t ld, int64_
                             double* Ainv, int64_t ldo);
 int set_identity(cudaStream_t st, double* A, int64_t ld, int64_t n);
 
+// small.cu -- the whole update in one single-CTA kernel for small problems
+constexpr int SMALL_P_MAX = 8, SMALL_K_MAX = 16;
+struct SmallStepCall {
+    int64_t p, k, J;
+    int rule, ts_kind;
+    double fixed_h, switch_;
+    const double *U, *G, *xi;
+    int64_t ldu, ldg, ldxi;
+    double* out;
+    int64_t ldo;
+    const double *y, *mu, *ustar, *bprior, *ginv_diag, *Ginv, *sinv_diag, *sig_diag, *Sinv, *Sigma0;
+    int64_t ldk, ldp;
+    double* S;
+    int* info;
+};
+bool small_step_eligible(int64_t p, int64_t k, int64_t J);
+int small_step(cudaStream_t st, const SmallStepCall& c);
+
 // forward.cu
 int exp_map(cudaStream_t st, const double* X, int64_t ldx, int64_t rows, int64_t cols, double* out, int64_t ldo);
 int elliptic_map(cudaStream_t st, const double* U, int64_t ldu, int64_t cols, double x1, double x2, double* G, int64_t ldg);

@@ -346,3 +346,32 @@ def test_run_with_a_pde_type_model(use_pool):
     assert _rel(s.Gstar, G[:3]) < 1e-8
     if pool is not None:
         assert len(s.Wall) == T + 1
+
+
+@pytest.mark.parametrize("d,k,J", [(2, 10, 100), (3, 5, 33), (8, 16, 512), (1, 1, 2)])
+def test_general_path_on_small_shapes(d, k, J, monkeypatch):
+    """Small problems normally take the single-kernel path (small.cu); the general multi-kernel path must give the
+    same answers on them (CES_NO_SMALL_PATH=1 is read when the handle is created)."""
+    monkeypatch.setenv("CES_NO_SMALL_PATH", "1")
+    pr = eo.linear_gaussian_problem(d, k, J, dense_gamma=True)
+    eng = Engine(d, k, J)
+    monkeypatch.delenv("CES_NO_SMALL_PATH")
+    eng2 = Engine(d, k, J)
+    try:
+        for e in (eng, eng2):
+            e.set_problem(pr["y"], pr["Gamma"], pr["Sigma0"], pr["mu"], pr["ustar"])
+        for rule in RULES + ("eki",):
+            o = eo.step(rule, pr["y"], pr["U0"], pr["G"], pr["Gamma"], pr["mu"], pr["Sigma0"], pr["ustar"], pr["xi"])
+            n0 = eng.launch_count()
+            Ua, ha, _ = eng.step_host(rule, pr["U0"], pr["G"], pr["xi"])
+            n1 = eng.launch_count()
+            Ub, hb, mb = eng2.step_host(rule, pr["U0"], pr["G"], pr["xi"])
+            n2 = eng.launch_count()
+            assert n2 - n1 == 1 and n1 - n0 > 5          # one kernel vs the general sequence
+            assert _rel(Ua, o["Uk"]) < TOL and _rel(Ub, o["Uk"]) < TOL, rule
+            assert abs(ha - o["hk"]) < TOL * o["hk"] and abs(hb - o["hk"]) < TOL * o["hk"]
+            for key in mb:
+                assert abs(mb[key] - o["metrics"][key]) <= TOL * abs(o["metrics"][key]), (rule, key)
+    finally:
+        eng.close()
+        eng2.close()
