@@ -721,7 +721,9 @@ int ces_step(ces_handle_t h, int rule, int ts_kind, double fixed_h, double switc
             if (ldo == h->Jl) CES_CUDA(cudaMemcpyAsync(h->pending_out, Uout, (size_t)h->pending_rows * wbytes, cudaMemcpyDeviceToHost, h->st));
             else CES_CUDA(cudaMemcpy2DAsync(h->pending_out, wbytes, Uout, ldo * sizeof(double), wbytes, h->pending_rows, cudaMemcpyDeviceToHost, h->st));
         }
-        CES_TRY(check_info(h, "cov(U)"));
+        CES_CUDA(cudaStreamSynchronize(h->st));
+        if (h->hS[S_INFO] != 0.0)
+            return fail(CES_ERR_NOT_SPD, "%s: matrix is not positive definite (pivot %lld)", "cov(U)", (long long)h->hS[S_INFO]);
         if (hk_host) *hk_host = h->hS[S_H];
         if (metrics_host) {
             const double J = (double)h->Jg;
@@ -759,9 +761,13 @@ int ces_step_host(ces_handle_t h, int rule, int ts_kind, double fixed_h, double 
         if (ld == J) return cudaMemcpyAsync(dst, src, (size_t)rows * wb, cudaMemcpyHostToDevice, s);
         return cudaMemcpy2DAsync(dst, pb, src, wb, wb, rows, cudaMemcpyHostToDevice, s);
     };
+    const bool small = h->use_small && formulation == CES_FORM_INTERACTION && small_step_eligible(h->p, h->k, h->Jl);
     // the noise is needed only by phase 4: upload it on a second stream while phases 1-3 compute
-    // (ordered after the previous step's use of the staging buffer through start_ev)
-    if (xi) {
+    // (ordered after the previous step's use of the staging buffer through start_ev); tiny problems keep
+    // everything on one stream -- the extra events would cost more than the copy
+    if (xi && small) {
+        CES_CUDA(h2d(h->stage_xi, xi, p, h->st));
+    } else if (xi) {
         CES_CUDA(cudaEventRecord(h->start_ev, h->st));
         CES_CUDA(cudaStreamWaitEvent(h->copy_st, h->start_ev, 0));
         CES_CUDA(h2d(h->stage_xi, xi, p, h->copy_st));
@@ -769,8 +775,7 @@ int ces_step_host(ces_handle_t h, int rule, int ts_kind, double fixed_h, double 
     }
     CES_CUDA(h2d(h->stage_U, U, p, h->st));
     CES_CUDA(h2d(h->stage_G, G, k, h->st));
-    if (h->use_small && formulation == CES_FORM_INTERACTION && small_step_eligible(h->p, h->k, h->Jl)) {
-        if (xi) CES_CUDA(cudaStreamWaitEvent(h->st, h->copy_ev, 0));
+    if (small) {
         h->pending_out = Uout;
         h->pending_rows = p;
         const int s1 = ces_step(h, rule, ts_kind, fixed_h, switch_, formulation, h->stage_U, ld, h->stage_G, ld,

@@ -47,6 +47,7 @@ enum StepScalars : int {
     S_BIAS_DATA = 4,  // sum_j (r_j^T Gamma^-1 r_j)^2
     S_MAXDRIFT = 5,   // max |drift| (aldi_constant)
     S_H = 6, S_SQRT2H = 7, S_NEG_H = 8, S_H_ALPHA = 9,
+    S_INFO = 15,      // small path: 1 + index of the first non-positive Cholesky pivot (0 = ok)
     S_COUNT = 16,
 };
 

@@ -197,6 +197,7 @@ __global__ void __launch_bounds__(512, 1) small_step_kernel(const SmallArgs a) {
         else h = 1.0 / (sqrt(red[0]) + 1e-8);
         sc[0] = h;
         sc[1] = sqrt(2.0 * h);
+        a.S[S_INFO] = 0.0;
         a.S[S_SSQ] = red[0]; a.S[S_SELF_BIAS] = red[1]; a.S[S_BIAS] = red[2]; a.S[S_SELF_DATA] = red[3]; a.S[S_BIAS_DATA] = red[4];
         a.S[S_MAXDRIFT] = maxdrift; a.S[S_H] = h; a.S[S_SQRT2H] = sc[1]; a.S[S_NEG_H] = -h; a.S[S_H_ALPHA] = h * alphaJ;
         // chol(C^uu) (:446, :487, :526), and chol(Sigma0 + h C) for the implicit prior step (:443)
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(512, 1) small_step_kernel(const SmallArgs a) {
                     }
                     for (int t = 0; t < c; ++t) x -= Lm[r * SP + t] * Lm[c * SP + t];
                     if (r == c) {
-                        if (!(x > 0.0)) atomicCAS(a.info, 0, r + 1);
+                        if (!(x > 0.0) && a.S[S_INFO] == 0.0) a.S[S_INFO] = (double)(r + 1);
                         Lm[r * SP + r] = sqrt(x);
                     } else {
                         Lm[r * SP + c] = x / Lm[c * SP + c];

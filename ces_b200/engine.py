@@ -288,7 +288,10 @@ class Engine(object):
         assert U.shape == (self.p, self.J) and G.shape == (self.k, self.J), (U.shape, G.shape)
         # a fresh array per call like the reference (callers keep references in Uall), in page-locked memory
         # from torch's caching host allocator so the device->host copy runs at full PCIe rate
-        out = self.torch.empty((self.p, self.J), dtype=self.torch.float64, pin_memory=True).numpy()
+        if U.nbytes >= (1 << 20):
+            out = self.torch.empty((self.p, self.J), dtype=self.torch.float64, pin_memory=True).numpy()
+        else:
+            out = np.empty_like(U)
         if xi is not None:
             xi = np.ascontiguousarray(xi, dtype=np.float64)
             assert xi.shape == U.shape
