@@ -132,7 +132,7 @@ def reference_arm(args):
                              "sample": sample, "extrapolated_full_J": full},
             "e2e": {"value": rate, "unit": "particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -177,8 +177,26 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """Print the one JSON line on the real stdout (see main: fd 1 is pointed at stderr while the run is in progress so
+    that library chatter such as NCCL's version banner cannot get in front of it)."""
+    text = json.dumps(line) + "\n"
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, text.encode())
+    else:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         reference_arm(args)
         return
@@ -342,7 +360,7 @@ def main():
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(d, k, J, Js)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

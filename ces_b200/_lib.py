@@ -25,7 +25,7 @@ EXPORTS = (
     "ces_step_host", "ces_forward_map", "ces_buffer", "ces_launch_count", "ces_gemm", "ces_potrf", "ces_posv",
     "ces_profile_enable", "ces_profile_read", "ces_darcy_create", "ces_darcy_destroy", "ces_darcy_forward",
     "ces_peek_step_size", "ces_phase3b_cpp", "ces_phase3c_resolve", "ces_phase3f_products", "ces_phase3f_finish",
-    "ces_fill_normal",
+    "ces_fill_normal", "ces_phase3_blocks",
 )
 
 _i64, _int, _dbl, _vp = ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_void_p
@@ -61,6 +61,7 @@ def load():
     lib.ces_phase2_centre.argtypes = [_vp, _int, _dp, _i64, _dp, _i64]
     lib.ces_phase3_interact.argtypes = [_vp, _int, _int]
     lib.ces_peek_step_size.argtypes = [_vp, _int, _dbl, ctypes.POINTER(_dbl)]
+    lib.ces_phase3_blocks.argtypes = [_vp, _int, _int, _int]
     lib.ces_phase3b_cpp.argtypes = [_vp]
     lib.ces_phase3f_products.argtypes = [_vp, _int]
     lib.ces_phase3f_finish.argtypes = [_vp, _int]

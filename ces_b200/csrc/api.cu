@@ -25,7 +25,7 @@ struct ces_handle_s {
     double *xi_pad = nullptr, *expU = nullptr;
     double *Cuu = nullptr, *L = nullptr, *Linv = nullptr, *M = nullptr, *Minv = nullptr, *cb = nullptr;
     double *D = nullptr, *ssq_partials = nullptr, *splitk_ws = nullptr;
-    int64_t ssq_cap = 0, splitk_cap = 0;
+    int64_t ssq_cap = 0, splitk_cap = 0, ssq_used = 0;
     int syrk_splits = 1;
     int* info = nullptr;
     // factored formulation (D never formed): P1 = U~ E^T, Gram matrices of E and W
@@ -341,14 +341,18 @@ int ces_phase2_centre(ces_handle_t h, int rule, const double* U, int64_t ldu, co
 }
 
 // D = (1/J) E^T Wsrc by source block s (rows of D) and column panel (K3, K4); V = U~ D (K5).
-static int interaction_loops(ces_handle_t h, const double* Wsrc, bool accumulate_ssq) {
+// Source blocks are taken in rotated order starting with this rank's own block ((rank + i) % nranks for
+// i in [first, first + count)), so the host can overlap the all-gather of the other ranks' E / U~ with block 0.
+static int interaction_loops(ces_handle_t h, const double* Wsrc, bool accumulate_ssq, int first, int count) {
     const int64_t p = h->p, k = h->k, ld = h->ldJ;
     cudaStream_t st = h->st;
-    int64_t npart = 0;
+    if (first == 0) h->ssq_used = 0;
+    int64_t npart = h->ssq_used;
     const double invJ = 1.0 / (double)h->Jg;
     for (int64_t c0 = 0; c0 < h->Jl; c0 += h->panel) {
         const int64_t nc = (h->Jl - c0) < h->panel ? (h->Jl - c0) : h->panel;
-        for (int s = 0; s < h->nranks; ++s) {
+        for (int i = first; i < first + count; ++i) {
+            const int s = (h->rank + i) % h->nranks;
             GemmCall g1;
             g1.a_mode = A_KM; g1.b_mode = B_KN;
             g1.M = (int)h->Jl; g1.N = (int)nc; g1.K = (int)k;
@@ -382,17 +386,35 @@ static int interaction_loops(ces_handle_t h, const double* Wsrc, bool accumulate
             g2.A = ut_block(h, s); g2.lda = ld;
             g2.B = h->D; g2.ldb = h->ldD;
             g2.C = h->V + c0; g2.ldc = ld;
-            g2.beta = (s == 0) ? 0.0 : 1.0;
+            g2.beta = (i == 0) ? 0.0 : 1.0;
             CES_TRY(gemm(st, g2));
         }
     }
-    if (accumulate_ssq) CES_TRY(sum_vector(st, h->ssq_partials, npart, h->S + S_SSQ));
+    h->ssq_used = npart;
+    if (accumulate_ssq && first + count == h->nranks) CES_TRY(sum_vector(st, h->ssq_partials, npart, h->S + S_SSQ));
     return CES_OK;
 }
+
+static int start_cholesky(ces_handle_t h, int rule);
 
 int ces_phase3_interact(ces_handle_t h, int rule, int skip_interaction) {
     CES_TRY(valid(h, true));
     if (rule != h->last_rule) return fail(CES_ERR_STATE, "phase3: rule differs from phase2%s", "");
+    CES_TRY(start_cholesky(h, rule));
+    if (skip_interaction) return CES_OK;       // 'constant' step size: D is formed once, by ces_phase3c_resolve
+    return interaction_loops(h, h->W, true, 0, h->nranks);
+}
+
+int ces_phase3_blocks(ces_handle_t h, int rule, int first, int count) {
+    CES_TRY(valid(h, true));
+    if (rule != h->last_rule) return fail(CES_ERR_STATE, "phase3: rule differs from phase2%s", "");
+    if (first < 0 || count < 0 || first + count > h->nranks) return fail(CES_ERR_INVALID, "phase3_blocks: bad block range%s", "");
+    if (first == 0) CES_TRY(start_cholesky(h, rule));
+    if (count == 0) return CES_OK;
+    return interaction_loops(h, h->W, true, first, count);
+}
+
+static int start_cholesky(ces_handle_t h, int rule) {
     const int64_t p = h->p;
     cudaStream_t st = h->st;
     // chol(C^uu)  (K7); EKI has no noise term and skips it.  Only the noise GEMM of phase 4 needs the factor, so it
@@ -414,8 +436,7 @@ int ces_phase3_interact(ces_handle_t h, int rule, int skip_interaction) {
         CES_CUDA(cudaEventRecord(h->chol_done, h->aux_st));
         h->chol_pending = true;
     }
-    if (skip_interaction) return CES_OK;       // 'constant' step size: D is formed once, by ces_phase3c_resolve
-    return interaction_loops(h, h->W, true);
+    return CES_OK;
 }
 
 int ces_peek_step_size(ces_handle_t h, int ts_kind, double fixed_h, double* hk_host) {
@@ -483,7 +504,7 @@ int ces_phase3c_resolve(ces_handle_t h, int rule) {
     g.A = h->MkInv; g.lda = h->ldk; g.B = h->R; g.ldb = ld; g.C = h->Wr; g.ldc = ld;
     CES_TRY(gemm(st, g));
     // the step size stays the one computed from the Gamma-only D (ces/calibrate.py:437 precedes :439-441)
-    return interaction_loops(h, h->Wr, false);
+    return interaction_loops(h, h->Wr, false, 0, h->nranks);
 }
 
 // ---- factored formulation: the same update without forming the J x J matrix -------------------------------------

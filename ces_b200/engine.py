@@ -80,12 +80,26 @@ def run_phases(phases, buffer, comm, p, k, rule, resolve=None, formulation="inte
                 allreduce(buffer(name))
         phases["finish_factored"]()
     else:
+        overlapped = False
         if comm is not None:
             allreduce(buffer("cuu"))
             e_all, ut_all = buffer("e_all"), buffer("ut_all")
-            dist.all_gather_into_tensor(e_all, e_all[rank * k:(rank + 1) * k].clone(), group=group)
-            dist.all_gather_into_tensor(ut_all, ut_all[rank * p:(rank + 1) * p].clone(), group=group)
-        phases["interact"](resolve == "always")
+            e_own, ut_own = e_all[rank * k:(rank + 1) * k], ut_all[rank * p:(rank + 1) * p]
+            if dist.get_backend(group) == "nccl" and resolve != "always" and "interact_own" in phases:
+                # NCCL: in-place all-gathers started asynchronously; the D / V GEMMs of this rank's own block (already
+                # in place after the centring phase) run while the other ranks' blocks arrive over NVLink
+                works = [dist.all_gather_into_tensor(e_all, e_own, group=group, async_op=True),
+                         dist.all_gather_into_tensor(ut_all, ut_own, group=group, async_op=True)]
+                phases["interact_own"]()
+                for wk in works:
+                    wk.wait()
+                phases["interact_rest"]()
+                overlapped = True
+            else:
+                dist.all_gather_into_tensor(e_all, e_own.clone(), group=group)
+                dist.all_gather_into_tensor(ut_all, ut_own.clone(), group=group)
+        if not overlapped:
+            phases["interact"](resolve == "always")
     if comm is not None:
         allreduce_slice(buffer("scalars"), 0, 5)
     keep = False
@@ -252,6 +266,8 @@ class Engine(object):
                 "sums": lambda: _lib.check(lib.ces_phase1_sums(h, Up, ldu, Gp, ldg)),
                 "centre": lambda: _lib.check(lib.ces_phase2_centre(h, r, Up, ldu, Gp, ldg)),
                 "interact": lambda skip: _lib.check(lib.ces_phase3_interact(h, r, 1 if skip else 0)),
+                "interact_own": lambda: _lib.check(lib.ces_phase3_blocks(h, r, 0, 1)),
+                "interact_rest": lambda: _lib.check(lib.ces_phase3_blocks(h, r, 1, self.nranks - 1)),
                 "peek": peek,
                 "cpp": lambda: _lib.check(lib.ces_phase3b_cpp(h)),
                 "resolve": lambda: _lib.check(lib.ces_phase3c_resolve(h, r)),

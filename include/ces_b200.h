@@ -99,6 +99,11 @@ int ces_set_problem(ces_handle_t h, const double* y_host, const double* Gamma_ho
 int ces_phase1_sums(ces_handle_t h, const double* U_dev, int64_t ldu, const double* G_dev, int64_t ldg);
 int ces_phase2_centre(ces_handle_t h, int rule, const double* U_dev, int64_t ldu, const double* G_dev, int64_t ldg);
 int ces_phase3_interact(ces_handle_t h, int rule, int skip_interaction);
+/* Phase 3 in pieces, for overlapping the all-gather with compute: source blocks (rows of D) are processed in rotated
+ * order (rank + i) % nranks, i in [first, first + count).  Block i = 0 is this rank's own E / U~ (already in place
+ * after phase 2), so the host starts the all-gathers asynchronously, calls ces_phase3_blocks(h, rule, 0, 1), waits for
+ * the collectives and calls ces_phase3_blocks(h, rule, 1, nranks - 1).  (first = 0 also starts chol(C^uu).) */
+int ces_phase3_blocks(ces_handle_t h, int rule, int first, int count);
 /* Non-default time_step modes ('constant', 'mix'; ces/calibrate.py:439-441, 470-473): after phase 3 (and its
  * all-reduce) ces_peek_step_size fixes and returns the step size hk this step uses; ces_phase3b_cpp forms the local
  * part of C^pp = cov(G, bias=True) = E E^T / J  [host: all-reduce(sum) of ces_buffer("cpp")]; ces_phase3c_resolve
