@@ -1,4 +1,5 @@
 // C ABI of libces_b200.so (include/ces_b200.h): handle, problem set-up, the phases of one update.
+#include <cmath>
 #include <cstring>
 #include <cstdlib>
 #include <string>
@@ -24,7 +25,7 @@ struct ces_handle_s {
     double *E_all = nullptr, *W = nullptr, *R = nullptr, *Ut_all = nullptr, *Z = nullptr, *Y = nullptr, *V = nullptr, *T = nullptr;
     double *xi_pad = nullptr, *expU = nullptr;
     double *Cuu = nullptr, *L = nullptr, *Linv = nullptr, *M = nullptr, *Minv = nullptr, *cb = nullptr;
-    double *D = nullptr, *ssq_partials = nullptr, *splitk_ws = nullptr;
+    double *D = nullptr, *ssq_partials = nullptr, *splitk_ws = nullptr, *v_ws = nullptr;
     int64_t ssq_cap = 0, splitk_cap = 0, ssq_used = 0;
     int syrk_splits = 1;
     int* info = nullptr;
@@ -387,6 +388,24 @@ static int interaction_loops(ces_handle_t h, const double* Wsrc, bool accumulate
             g2.B = h->D; g2.ldb = h->ldD;
             g2.C = h->V + c0; g2.ldc = ld;
             g2.beta = (i == 0) ? 0.0 : 1.0;
+            // wave quantisation: d/128 x nc/128 tiles of a long contraction rarely fill 148 SMs evenly (e.g. 512 tiles
+            // = 3.46 waves); splitting the contraction 2-4 ways makes the tail negligible
+            {
+                const double tiles = (double)gemm_tiles(g2.M, g2.N);
+                int best = 1;
+                double best_eff = 0.0;
+                for (int sp = 1; sp <= 4; ++sp) {
+                    const double waves = tiles * sp / 148.0;
+                    const double eff = waves / ceil(waves);
+                    if (eff > best_eff + 0.02) { best_eff = eff; best = sp; }
+                    if (best_eff >= 0.97) break;
+                }
+                if (best > 1 && g2.K >= 64 * best) {
+                    if (!h->v_ws) CES_TRY(dalloc(h, &h->v_ws, 4 * p * h->panel));
+                    g2.splits = best;
+                    g2.splitk_ws = h->v_ws;
+                }
+            }
             CES_TRY(gemm(st, g2));
         }
     }

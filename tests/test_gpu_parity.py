@@ -375,3 +375,18 @@ def test_general_path_on_small_shapes(d, k, J, monkeypatch):
     finally:
         eng.close()
         eng2.close()
+
+
+def test_split_contraction_of_the_drift_product():
+    """d = 1024, J = 8192 gives 8 x 64 = 512 tiles for V = U~ D (3.46 waves of 148 SMs): the library splits the
+    contraction; the result must not change beyond rounding."""
+    d, k, J = 1024, 24, 8192
+    pr = eo.linear_gaussian_problem(d, k, J)
+    o = eo.step("aldi", pr["y"], pr["U0"], pr["G"], pr["Gamma"], pr["mu"], pr["Sigma0"], pr["ustar"], pr["xi"])
+    eng = Engine(d, k, J)
+    try:
+        eng.set_problem(pr["y"], pr["Gamma"], pr["Sigma0"], pr["mu"], pr["ustar"])
+        Uk, hk, met = eng.step_host("aldi", pr["U0"], pr["G"], pr["xi"])
+        assert _rel(Uk, o["Uk"]) < TOL and abs(hk - o["hk"]) < TOL * hk
+    finally:
+        eng.close()
