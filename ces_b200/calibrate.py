@@ -461,7 +461,8 @@ class sampling(enka):
             # an unknown ``update`` leaves the ensemble unchanged and records nothing, like :364-369 --
             # the reference then fails on the empty ``metrics['t']``; so do we
             if save_online:
-                tag = model.model_name + '-eks-' + str(model.l_window).zfill(3) + '-' + str(self.J).zfill(4)
+                # the reference reads model.l_window here (:375-376), which its own Darcy model lacks; default it
+                tag = model.model_name + '-eks-' + str(getattr(model, 'l_window', 0)).zfill(3) + '-' + str(self.J).zfill(4)
                 if hasattr(self, 'nexp'):
                     tag += '-' + str(self.nexp).zfill(2)
                 if eng.rank == 0:

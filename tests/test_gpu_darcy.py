@@ -94,3 +94,29 @@ def test_eks_run_on_darcy_matches_oracle_loop():
     assert _rel(s.Ustar, U) < 1e-6          # three chained steps through an iterative PDE solve
     assert abs(s.metrics["t"][-1] - t) < 1e-7 * t
     assert s.Gall.shape == (T + 1, n_obs, J)
+
+
+def test_darcy_flow_example_script(tmp_path, monkeypatch):
+    """examples/darcy_flow.py (the reference's examples/scripts/darcy-flow.py scenario) runs end to end, reduces the
+    data misfit, stops on t_tol and writes the online files the reference writes."""
+    import importlib.util
+    import os
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("darcy_flow_example", os.path.join(root, "examples", "darcy_flow.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setattr(sys, "argv", ["darcy_flow.py", "--nmesh", "16", "--T", "12", "--t-tol", "0.05", "--sizes", "17,64",
+                                      "--save-online"])
+    neks = mod.main()
+    for key, (eks,) in neks.items():
+        m = eks.metrics
+        assert len(m["t"]) <= 12 and (m["t"][-1] > 0.05 or len(m["t"]) == 12)
+        assert m["bias-data"][-1] < m["bias-data"][0]
+        assert eks.Ustar.shape == (256, eks.J) and eks.Gstar.shape == (50, eks.J)
+        assert np.isfinite(eks.Ustar).all()
+        d = os.path.join(str(tmp_path), "ensembles", "darcy-flow-eks-000-%s-00" % str(eks.J).zfill(4))
+        files = sorted(os.listdir(d))
+        assert "metrics.pkl" in files and "ensemble_0000.npy" in files and "Gensemble_0000.npy" in files
