@@ -42,7 +42,7 @@ import pickle
 
 import numpy as np
 
-from .engine import Engine, shard_range
+from .engine import Engine
 
 _METRIC_KEYS = ("self-bias", "self-bias-data", "bias-data", "bias", "t")
 _RULE_METHOD = {"eks": "eks_update", "aldi": "eks_update_aldi", "aldi_constant": "eks_update_aldi_constant",

@@ -752,7 +752,7 @@ int ces_step(ces_handle_t h, int rule, int ts_kind, double fixed_h, double switc
         c.ginv_diag = h->gamma_diag ? h->ginv_diag : nullptr; c.Ginv = h->gamma_diag ? nullptr : h->Ginv;
         c.sinv_diag = h->sinv_diag; c.sig_diag = h->sig_diag;
         c.Sinv = h->sigma_diag ? nullptr : h->Sinv; c.Sigma0 = h->sigma_diag ? nullptr : h->Sigma0;
-        c.ldk = h->ldk; c.ldp = h->ldp; c.S = h->S; c.info = h->info;
+        c.ldk = h->ldk; c.ldp = h->ldp; c.S = h->S;
         h->last_rule = rule;
         CES_TRY(small_step(h->st, c));
         CES_CUDA(cudaMemcpyAsync(h->hS, h->S, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, h->st));

@@ -109,7 +109,6 @@ struct SmallStepCall {
     const double *y, *mu, *ustar, *bprior, *ginv_diag, *Ginv, *sinv_diag, *sig_diag, *Sinv, *Sigma0;
     int64_t ldk, ldp;
     double* S;
-    int* info;
 };
 bool small_step_eligible(int64_t p, int64_t k, int64_t J);
 int small_step(cudaStream_t st, const SmallStepCall& c);

@@ -22,8 +22,7 @@ struct SmallArgs {
     const double *ginv_diag, *Ginv;      // one of them (diagonal / dense Gamma^-1, ld = ldk)
     const double *sinv_diag, *sig_diag, *Sinv, *Sigma0;   // diagonal or dense prior (ld = ldp)
     long long ldk, ldp;
-    double* S;                           // device scalars (StepScalars layout)
-    int* info;
+    double* S;                           // device scalars (StepScalars layout; S_INFO reports a failed pivot)
 };
 
 __device__ __forceinline__ void block_reduce5(double (&v)[5], double (*scratch)[32], bool take_max4) {
@@ -301,7 +300,7 @@ int small_step(cudaStream_t st, const SmallStepCall& c) {
     a.y = c.y; a.mu = c.mu; a.ustar = c.ustar; a.bprior = c.bprior;
     a.ginv_diag = c.ginv_diag; a.Ginv = c.Ginv; a.sinv_diag = c.sinv_diag; a.sig_diag = c.sig_diag;
     a.Sinv = c.Sinv; a.Sigma0 = c.Sigma0; a.ldk = c.ldk; a.ldp = c.ldp;
-    a.S = c.S; a.info = c.info;
+    a.S = c.S;
     const int threads = (int)round_up(c.J, 32);
     const size_t smem = ((size_t)(c.k + c.p) * c.J + (SK + SP) + 3 * SP * SP + SP + 8) * sizeof(double);
     static size_t configured = 0;

@@ -11,6 +11,14 @@ import torch
 pytestmark = pytest.mark.gpu
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    import socket
+
+    with socket.socket() as sock:
+        sock.bind(("127.0.0.1", 0))
+        return sock.getsockname()[1]
 ROOT = os.path.dirname(HERE)
 
 
@@ -64,7 +72,7 @@ def test_two_gpu_step_matches_oracle(rule, J):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + (os.getpid() + J) % 1000
+    port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, world, port, rule, 24, 40, J, q)) for r in range(world)]
     for p in procs:
         p.start()

@@ -12,6 +12,14 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    import socket
+
+    with socket.socket() as sock:
+        sock.bind(("127.0.0.1", 0))
+        return sock.getsockname()[1]
 ROOT = os.path.dirname(HERE)
 
 
@@ -58,7 +66,7 @@ def test_sharded_orchestration_matches_single_process(world, rule, J, ts, t_last
         ts, formulation = None, "factored"
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() + J + len(str(ts)) * 7 + int((t_last or 0) * 10)) % 2000
+    port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, world, port, rule, 5, 7, J, q, ts, t_last, formulation))
              for r in range(world)]
     for p in procs:
