@@ -368,9 +368,10 @@ def main():
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the D GEMM from the committed ncu capture
 # (profiles/); None until a capture for that workload exists.
 TRAFFIC_BYTES = {
-    # profiles/r01_ncu_full_gemm_d_cfg3.csv: 12.96 GB read + 2.14 GB written for the 16384 x 16384 x 4096 launch
-    # (algorithmic: E 0.54 + W 0.54 + D 2.15 GB; the excess is E/W panel re-reads that miss the L2, hit rate 81.7 %)
-    "cfg3": 15.10e9,
+    # profiles/r01_gemm_raster_sweep.csv (group 16): 12.39 GB read + 2.14 GB written for the 16384 x 16384 x 4096 launch
+    # (algorithmic: E 0.54 + W 0.54 + D 2.15 GB; the excess is E/W panels streamed once per wave of 148 tiles: a wave's
+    # unique footprint, ~100 MB, fills the L2, so there is no cross-wave reuse; 3 % of HBM bandwidth, duration unchanged)
+    "cfg3": 14.53e9,
 }
 
 if __name__ == "__main__":
