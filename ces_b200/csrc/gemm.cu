@@ -44,7 +44,7 @@ int gemm(cudaStream_t st, const GemmCall& c) {
     a.tiles_m = (int)ceil_div(c.M, GEMM_BM);
     a.tiles_n = (int)ceil_div(c.N, GEMM_BN);
     static const int env_group = []() { const char* e = std::getenv("CES_GEMM_GROUP_M"); return e ? atoi(e) : 0; }();
-    a.group_m = c.group_m > 0 ? c.group_m : (env_group > 0 ? env_group : 8);
+    a.group_m = c.group_m > 0 ? c.group_m : (env_group > 0 ? env_group : 16);
     a.flags = c.flags;
     a.splits = 1;
     a.kblocks_per_split = 0;
