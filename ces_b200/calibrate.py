@@ -123,7 +123,7 @@ class enka(object):
             padded = np.empty((theta.shape[0], width))
             padded[:, :n] = theta
             padded[:, n:] = theta[:, -1:]
-            eng = Engine(theta.shape[0], self.n_obs, width)
+            eng = Engine(theta.shape[0], self.n_obs, width, d_panel_bytes=-1)       # forward maps only
             try:
                 U = torch.from_numpy(padded).cuda()
                 G = torch.empty(self.n_obs, width, dtype=torch.float64, device="cuda")
@@ -267,9 +267,16 @@ class sampling(enka):
 
     @staticmethod
     def _frobenius(D):
+        import ctypes
         import torch
+        from . import _lib
 
-        return float(torch.linalg.matrix_norm(torch.from_numpy(np.ascontiguousarray(D, dtype=np.float64)).cuda()))
+        Dd = torch.from_numpy(np.ascontiguousarray(D, dtype=np.float64)).cuda()
+        out = ctypes.c_double()
+        _lib.check(_lib.load().ces_frobenius(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream),
+                                             ctypes.c_void_p(Dd.data_ptr()), int(Dd.stride(0)), int(Dd.shape[0]),
+                                             int(Dd.shape[1]), ctypes.byref(out)))
+        return out.value
 
     def _advance_time(self, hk):
         # ces/calibrate.py:262-265 (first step <=> no time recorded yet)

@@ -15,6 +15,7 @@ struct ces_handle_s {
     int64_t ldJ = 0, ldp = 0, ldk = 0, ldD = 0, panel = 0;
     cudaStream_t st = nullptr;
     bool have_problem = false, gamma_diag = true, sigma_diag = true;
+    bool forward_only = false;          // created for ces_forward_map only: no update workspace
     bool use_small = true;              // single-kernel path for small problems (CES_NO_SMALL_PATH=1 disables it)
     int last_rule = -1;
     // problem data (device)
@@ -124,6 +125,7 @@ int device_spd_inverse(ces_handle_t h, const double* host, int64_t n, double* ds
 
 int valid(ces_handle_t h, bool need_problem) {
     if (!h) return fail(CES_ERR_INVALID, "null handle%s", "");
+    if (need_problem && h->forward_only) return fail(CES_ERR_STATE, "this handle was created for forward maps only%s", "");
     if (need_problem && !h->have_problem) return fail(CES_ERR_STATE, "ces_set_problem has not been called%s", "");
     return CES_OK;
 }
@@ -153,6 +155,7 @@ int ces_create(int64_t p, int64_t k, int64_t J_local, int64_t J_global, int rank
     h->ldJ = padded_ld(J_local);
     h->ldp = padded_ld(p);
     h->ldk = padded_ld(k);
+    h->forward_only = d_panel_bytes < 0;
     if (d_panel_bytes <= 0) d_panel_bytes = 8ll << 30;
     int64_t panel = d_panel_bytes / (8 * h->ldJ);
     panel = panel / 128 * 128;
@@ -178,7 +181,7 @@ int ces_create(int64_t p, int64_t k, int64_t J_local, int64_t J_global, int rank
         h->syrk_splits = (int)sp;
         h->splitk_cap = sp * p * p;
     }
-#define A_(ptr, n) if (s == CES_OK) s = dalloc(h, &h->ptr, (n))
+#define A_(ptr, n) if (s == CES_OK && !h->forward_only) s = dalloc(h, &h->ptr, (n))
     A_(y, k); A_(ginv_diag, k); A_(mu, p); A_(ustar, p); A_(sinv_diag, p); A_(sig_diag, p); A_(bprior, p);
     A_(sums, k + p); A_(cvec, k); A_(zvec, k); A_(S, S_COUNT); A_(cb, p);
     A_(qpart, 2 * (int64_t)ny * h->ldJ); A_(formpart, 2 * ceil_div(h->ldJ, 256) + 2); A_(rowscratch, (p > k ? p : k));
@@ -226,6 +229,7 @@ int ces_destroy(ces_handle_t h) {
 int ces_set_problem(ces_handle_t h, const double* y, const double* Gamma, const double* Sigma0, const double* mu,
                     const double* ustar) {
     CES_TRY(valid(h, false));
+    if (h->forward_only) return fail(CES_ERR_STATE, "this handle was created for forward maps only%s", "");
     if (!y || !Gamma || !Sigma0 || !mu || !ustar) return fail(CES_ERR_INVALID, "ces_set_problem: null pointer%s", "");
     const int64_t p = h->p, k = h->k;
     h->have_problem = false;
@@ -929,6 +933,21 @@ int ces_fill_normal(void* stream, uint64_t seed, uint64_t step, double* X, int64
                     int64_t col_offset) {
     if (!X || ld < cols) return fail(CES_ERR_INVALID, "ces_fill_normal: bad argument%s", "");
     return fill_normal(static_cast<cudaStream_t>(stream), X, ld, rows, cols, col_offset, seed, step);
+}
+
+int ces_frobenius(void* stream, const double* X, int64_t ld, int64_t rows, int64_t cols, double* out_host) {
+    if (!X || !out_host || rows < 1 || cols < 1 || ld < cols) return fail(CES_ERR_INVALID, "ces_frobenius: bad argument%s", "");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double* part = nullptr;
+    CES_CUDA(cudaMalloc(&part, (size_t)(rows + 1) * sizeof(double)));
+    int s = row_sumsq(st, X, ld, rows, cols, part);
+    if (s == CES_OK) s = sum_vector(st, part, rows, part + rows);
+    double v = 0.0;
+    if (s == CES_OK && cudaMemcpyAsync(&v, part + rows, sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) s = CES_ERR_CUDA;
+    if (cudaStreamSynchronize(st) != cudaSuccess && s == CES_OK) s = fail(CES_ERR_CUDA, "ces_frobenius: kernel failure%s", "");
+    cudaFree(part);
+    if (s == CES_OK) *out_host = sqrt(v);
+    return s;
 }
 
 int ces_gemm(void* stream, int a_mode, int b_mode, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,

@@ -241,6 +241,22 @@ int finish_forms(cudaStream_t st, const double* qpart, int ny, int64_t ld, int64
     return CES_OK;
 }
 
+// out[r] = sum_j X[r, j]^2  (rows of a matrix whose Frobenius norm is wanted: timestep_method(D, ...), :248)
+__global__ void __launch_bounds__(256) row_sumsq_kernel(const double* __restrict__ X, long long ld, long long cols,
+                                                        double* __restrict__ out) {
+    __shared__ double scratch[32];
+    const double* row = X + (size_t)blockIdx.x * ld;
+    double s = 0.0;
+    for (long long i = threadIdx.x; i < cols; i += 256) s += row[i] * row[i];
+    const double t = block_sum(s, scratch);
+    if (threadIdx.x == 0) out[blockIdx.x] = t;
+}
+int row_sumsq(cudaStream_t st, const double* X, int64_t ld, int64_t rows, int64_t cols, double* out) {
+    row_sumsq_kernel<<<(unsigned)rows, 256, 0, st>>>(X, ld, cols, out);
+    CES_LAUNCHED(1);
+    return CES_OK;
+}
+
 // out[0] = sum of n doubles, fixed order (one CTA).
 __global__ void __launch_bounds__(1024) sum_vector_kernel(const double* __restrict__ v, long long n, double* __restrict__ out) {
     __shared__ double scratch[32];

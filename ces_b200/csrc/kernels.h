@@ -65,6 +65,7 @@ int data_forms(cudaStream_t st, const double* E, const double* W, int64_t ld, in
 int finish_forms(cudaStream_t st, const double* qpart, int ny, int64_t ld, int64_t cols, bool square, double* part,
                  double* out);
 int sum_vector(cudaStream_t st, const double* v, int64_t n, double* out);
+int row_sumsq(cudaStream_t st, const double* X, int64_t ld, int64_t rows, int64_t cols, double* out);
 int matvec(cudaStream_t st, const double* M, int64_t ld, int64_t n, const double* x, double* y);
 int scale_vector(cudaStream_t st, const double* d, const double* x, double* y, int64_t n);
 int step_scalars(cudaStream_t st, double* S, int kind, double fixed_h, double alpha_J);

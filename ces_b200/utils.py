@@ -35,7 +35,7 @@ class _DeviceMap(object):
         theta = np.asarray(theta, dtype=np.float64).reshape(-1)
         p = theta.shape[0]
         # a handle needs at least two particles: evaluate a 2-column ensemble and keep column 0
-        eng = Engine(p, n_obs, 2)
+        eng = Engine(p, n_obs, 2, d_panel_bytes=-1)       # forward maps only
         try:
             U = torch.from_numpy(np.stack([theta, theta], axis=1)).cuda()
             G = torch.empty(n_obs, 2, dtype=torch.float64, device="cuda")

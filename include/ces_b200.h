@@ -72,7 +72,8 @@ const char* ces_last_error(void);
  * column sharding (1 GPU: J_local = J_global, rank 0 of 1).  With nranks > 1 every rank must use the
  * same J_local (pad the last shard with zero columns and pass its true width to the phases through
  * `cols_local`).  `stream` is a cudaStream_t (NULL = legacy default stream).  `d_panel_bytes` bounds the
- * workspace of the J x J interaction matrix, which is formed in column panels (0 = 8 GiB default). */
+ * workspace of the J x J interaction matrix, which is formed in column panels (0 = 8 GiB default; < 0 = a
+ * light handle for ces_forward_map only, without any update workspace). */
 int ces_create(int64_t p, int64_t k, int64_t J_local, int64_t J_global, int rank, int nranks, int64_t cols_local,
                void* stream, int64_t d_panel_bytes, ces_handle_t* out);
 int ces_destroy(ces_handle_t h);
@@ -168,6 +169,9 @@ int ces_darcy_create(int64_t N, int64_t p, const double* PhiT_host, const double
 int ces_darcy_destroy(void* model);
 int ces_darcy_forward(void* model, const double* U_dev, int64_t ldu, int64_t cols, double* G_dev, int64_t ldg,
                       int full_solution, double tol, int max_iter, int* iters_host);
+
+/* Frobenius norm of a device matrix (sampling.timestep_method(D, ...) for callers that own an explicit D). */
+int ces_frobenius(void* stream, const double* X_dev, int64_t ld, int64_t rows, int64_t cols, double* out_host);
 
 /* N(0,1) noise on the device (production alternative to the host draw np.random.normal(0,1,[p,J]) of
  * ces/calibrate.py:447,488,527): Philox4x32-10 + Box-Muller.  Element (row, col_offset + col) depends only on

@@ -390,3 +390,21 @@ def test_split_contraction_of_the_drift_product():
         assert _rel(Uk, o["Uk"]) < TOL and abs(hk - o["hk"]) < TOL * hk
     finally:
         eng.close()
+
+
+def test_timestep_method_with_an_explicit_interaction_matrix():
+    """sampling.timestep_method(D, ...) for callers that own D (ces/calibrate.py:243-267): default rule, the time
+    bookkeeping, 'constant' and 'mix'."""
+    rng = np.random.default_rng(3)
+    D = rng.standard_normal((37, 37))
+    s = calibrate.sampling(2, 3, 37)
+    s.T = 30
+    s._ensure_metrics()
+    h1 = s.timestep_method(D, None, None, None, None)
+    assert abs(h1 - eo.timestep(D)) < 1e-14 * h1 and s.metrics["t"] == [h1]
+    h2 = s.timestep_method(D, None, None, None, None, time_step="constant")
+    assert h2 == 1. / 15 and abs(s.metrics["t"][-1] - (h1 + h2)) < 1e-15
+    h3 = s.timestep_method(D, None, None, None, None, time_step="mix", spinup=0.01, delta_t=0.25)
+    assert h3 == 0.25
+    with pytest.raises(NotImplementedError):
+        s.timestep_method(D, None, None, None, None, time_step="spectral")
