@@ -408,3 +408,36 @@ def test_timestep_method_with_an_explicit_interaction_matrix():
     assert h3 == 0.25
     with pytest.raises(NotImplementedError):
         s.timestep_method(D, None, None, None, None, time_step="spectral")
+
+
+def test_target_size_properties():
+    """BASELINE.json's target shape (d=1024, k=4096, J=65536; D is formed in 4 column panels): step size through
+    the Gram identity and a 128-particle probe of U_{n+1} recomputed from the definition with torch fp64 (cuBLAS)."""
+    d, k, J = 1024, 4096, 65536
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    rn = lambda *s: torch.randn(*s, dtype=torch.float64, device="cuda", generator=gen)
+    A = rn(k, d) / d ** 0.5
+    ustar = rn(d)
+    y = A @ ustar + 0.1 * rn(k)
+    U = 10.0 * rn(d, J)
+    G = A @ U
+    xi = rn(d, J)
+    eng = Engine(d, k, J)
+    try:
+        eng.set_problem(y.cpu().numpy(), 0.01 * np.eye(k), 100.0 * np.eye(d), np.zeros(d), ustar.cpu().numpy())
+        out, hk, met = eng.step("aldi", U, G, xi)
+        E = G - G.mean(dim=1, keepdim=True)
+        W = (G - y[:, None]) / 0.01
+        frob2 = float(((E @ E.t()) * (W @ W.t())).sum()) / J ** 2
+        h_ref = 1.0 / (frob2 ** 0.5 + 1e-8)
+        assert abs(hk - h_ref) < 1e-10 * h_ref
+        cols = torch.randperm(J, device="cuda", generator=gen)[:128]
+        Ut = U - U.mean(dim=1, keepdim=True)
+        Dc = (E.t() @ W[:, cols]) / J
+        C = (Ut @ Ut.t()) / (J - 1) + 1e-8 * torch.eye(d, dtype=torch.float64, device="cuda")
+        L = torch.linalg.cholesky(C)
+        ref = (U[:, cols] - hk * (Ut @ Dc) - hk * (C @ (U[:, cols] / 100.0)) + hk * (d + 1.0) / J * Ut[:, cols]
+               + (2 * hk) ** 0.5 * (L @ xi[:, cols]))
+        assert float((out[:, cols] - ref).abs().max() / ref.abs().max()) < TOL
+    finally:
+        eng.close()
