@@ -372,6 +372,9 @@ TRAFFIC_BYTES = {
     # (algorithmic: E 0.54 + W 0.54 + D 2.15 GB; the excess is E/W panels streamed once per wave of 148 tiles: a wave's
     # unique footprint, ~100 MB, fills the L2, so there is no cross-wave reuse; 3 % of HBM bandwidth, duration unchanged)
     "cfg3": 14.53e9,
+    # profiles/r01_ncu_full_gemm_d_target.csv: 56.98 GB read + 8.59 GB written per 65536 x 16384 x 4096 panel launch
+    # (algorithmic: E 2.15 + W panel 0.54 + D panel 8.59 GB), same mechanism, 3.3 % of HBM bandwidth
+    "target": 65.57e9,
 }
 
 if __name__ == "__main__":
