@@ -368,12 +368,13 @@ def main():
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the D GEMM from the committed ncu capture
 # (profiles/); None until a capture for that workload exists.
 TRAFFIC_BYTES = {
-    # profiles/r01_gemm_raster_sweep.csv (group 16): 12.39 GB read + 2.14 GB written for the 16384 x 16384 x 4096 launch
+    # profiles/r01_gemm_raster_sweep.csv (group 16, serpentine K): 9.53 GB read + 2.14 GB written for the 16384 x 16384 x 4096 launch
     # (algorithmic: E 0.54 + W 0.54 + D 2.15 GB; the excess is E/W panels streamed once per wave of 148 tiles: a wave's
     # unique footprint, ~100 MB, fills the L2, so there is no cross-wave reuse; 3 % of HBM bandwidth, duration unchanged)
-    "cfg3": 14.53e9,
+    "cfg3": 11.67e9,
     # profiles/r01_ncu_full_gemm_d_target.csv: 56.98 GB read + 8.59 GB written per 65536 x 16384 x 4096 panel launch
-    # (algorithmic: E 2.15 + W panel 0.54 + D panel 8.59 GB), same mechanism, 3.3 % of HBM bandwidth
+    # (algorithmic: E 2.15 + W panel 0.54 + D panel 8.59 GB), same mechanism, 3.3 % of HBM bandwidth; captured before
+    # the serpentine traversal (-23 % reads at cfg3)
     "target": 65.57e9,
 }
 

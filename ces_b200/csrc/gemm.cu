@@ -49,6 +49,18 @@ int gemm(cudaStream_t st, const GemmCall& c) {
     a.splits = 1;
     a.kblocks_per_split = 0;
     a.splitk_ws = nullptr;
+    {
+        static int sms = 0;
+        if (!sms) {
+            int dev = 0;
+            if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1)
+                sms = 148;
+        }
+        a.wave_ctas = sms;
+        static const int env_serp = []() { const char* e = std::getenv("CES_GEMM_SERPENTINE"); return e ? atoi(e) : -1; }();
+        // default on: -23 % DRAM reads on the D GEMM (profiles/r01_gemm_raster_sweep.csv); CES_GEMM_SERPENTINE=0 disables
+        if (env_serp != 0) a.flags |= GEMM_SERPENTINE_K;
+    }
     a.a_batch_rows = (int)c.a_batch_rows; a.b_batch_rows = (int)c.b_batch_rows; a.c_batch_elems = c.c_batch_elems;
     const int kb_total = (int)ceil_div(c.K, GEMM_BK);
     int splits = c.splits > 1 ? c.splits : 1;

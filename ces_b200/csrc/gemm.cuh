@@ -50,6 +50,7 @@ struct GemmArgs {
     // and writes C + z*c_batch_elems.  A batched operand must fill whole TMA boxes along its row axis.
     int a_batch_rows, b_batch_rows;
     long long c_batch_elems;
+    int wave_ctas;             // CTAs resident at once (SM count); used by GEMM_SERPENTINE_K
 };
 
 // Byte offset of element (row r, contraction index kk) in a contraction-contiguous 128x16 tile.
@@ -109,6 +110,9 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         kb_end = min(kb_total, kb_begin + args.kblocks_per_split);
     }
     const int nkb = max(kb_end - kb_begin, 0);
+    // Alternate waves of CTAs walk the contraction axis in opposite directions: when a wave ends the L2 holds the
+    // high-k part of its panels, which is exactly where the next wave (sharing the group's A panels) then starts.
+    const bool reverse_k = (args.flags & GEMM_SERPENTINE_K) && (((int)blockIdx.x / args.wave_ctas) & 1);
 
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t full0 = smem_u32(bar_full), empty0 = smem_u32(bar_empty);
@@ -138,7 +142,7 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 mbar_expect_tx(fb, GEMM_STAGE_BYTES);
                 const uint32_t a_dst = smem_base + s * GEMM_STAGE_BYTES;
                 const uint32_t b_dst = a_dst + GEMM_TILE_BYTES;
-                const int k0 = (kb_begin + it) * GEMM_BK;
+                const int k0 = (reverse_k ? (kb_end - 1 - it) : (kb_begin + it)) * GEMM_BK;
                 const int az = (int)blockIdx.y * args.a_batch_rows, bz = (int)blockIdx.y * args.b_batch_rows;
                 if (A_MODE == 0) {
                     tma_load_2d(a_dst, &mapA, fb, k0, m0 + az);

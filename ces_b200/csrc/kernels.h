@@ -12,6 +12,7 @@ enum GemmFlags : int {
     GEMM_A_LOWER_TRI = 1,    // A (MK) is lower triangular: rows of tile tm need kk < (tm+1)*BM only
     GEMM_C_LOWER_ONLY = 2,   // compute only tiles with tn <= tm (symmetric result)
     GEMM_B_UPPER_TRI = 4,    // B (KN) is upper triangular: columns of tile tn need kk < (tn+1)*BN only
+    GEMM_SERPENTINE_K = 8,   // odd waves of CTAs traverse the contraction axis backwards (L2 reuse across waves)
 };
 
 enum AMode : int { A_MK = 0, A_KM = 1 };
