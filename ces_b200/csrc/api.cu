@@ -27,7 +27,7 @@ struct ces_handle_s {
     double *xi_pad = nullptr, *expU = nullptr;
     double *Cuu = nullptr, *L = nullptr, *Linv = nullptr, *M = nullptr, *Minv = nullptr, *cb = nullptr;
     double *D = nullptr, *ssq_partials = nullptr, *splitk_ws = nullptr, *v_ws = nullptr;
-    int64_t ssq_cap = 0, splitk_cap = 0, ssq_used = 0;
+    int64_t ssq_cap = 0, splitk_cap = 0, ssq_used = 0, v_ws_planes = 4;
     int syrk_splits = 1;
     int* info = nullptr;
     // factored formulation (D never formed): P1 = U~ E^T, Gram matrices of E and W
@@ -157,12 +157,15 @@ int ces_create(int64_t p, int64_t k, int64_t J_local, int64_t J_global, int rank
     h->ldk = padded_ld(k);
     h->forward_only = d_panel_bytes < 0;
     if (d_panel_bytes <= 0) d_panel_bytes = 8ll << 30;
-    int64_t panel = d_panel_bytes / (8 * h->ldJ);
+    // multi-rank: the D blocks of the other ranks' particles are formed by ONE batched launch, one slot each
+    const int64_t slots = nranks > 1 ? nranks - 1 : 1;
+    int64_t panel = d_panel_bytes / (8 * h->ldJ * slots);
     panel = panel / 128 * 128;
     if (panel < 128) panel = 128;
     if (panel > h->ldJ) panel = h->ldJ;
     h->panel = panel;
     h->ldD = panel;
+    h->v_ws_planes = slots > 4 ? slots : 4;
 
     int s = CES_OK;
     const int nyk0 = form_row_blocks(k, h->ldJ), nyp0 = form_row_blocks(p, h->ldJ);
@@ -188,7 +191,7 @@ int ces_create(int64_t p, int64_t k, int64_t J_local, int64_t J_global, int rank
     A_(E_all, (int64_t)nranks * k * h->ldJ); A_(W, k * h->ldJ);
     A_(Ut_all, (int64_t)nranks * p * h->ldJ); A_(Z, p * h->ldJ); A_(V, p * h->ldJ); A_(T, p * h->ldJ);
     A_(Cuu, p * h->ldp); A_(L, p * h->ldp); A_(Linv, round_up(p, CHOL_NB) * kLinvLd);
-    A_(D, h->ldJ * h->ldD);
+    A_(D, slots * h->ldJ * h->ldD);
     A_(ssq_partials, h->ssq_cap); A_(splitk_ws, h->splitk_cap);
 #undef A_
     if (s == CES_OK) {
@@ -346,8 +349,12 @@ int ces_phase2_centre(ces_handle_t h, int rule, const double* U, int64_t ldu, co
 }
 
 // D = (1/J) E^T Wsrc by source block s (rows of D) and column panel (K3, K4); V = U~ D (K5).
-// Source blocks are taken in rotated order starting with this rank's own block ((rank + i) % nranks for
-// i in [first, first + count)), so the host can overlap the all-gather of the other ranks' E / U~ with block 0.
+// Source blocks (rows of D = particles of rank s) are taken in rotated order starting with this rank's own block:
+// positions i in [first, first + count) map to s = (rank + i) % nranks, so the host can overlap the all-gather of the
+// other ranks' E / U~ with position 0.  Consecutive positions whose s is contiguous in memory are processed by ONE
+// batched D launch (blockIdx.y = block, one D slot each) and ONE batched V launch whose per-block partial products are
+// summed by the split-K reduce kernel -- with P = 8 ranks and small shards a per-block launch has too few tiles to
+// fill 148 SMs (256 tiles = 1.73 waves at Jl = 2048).
 static int interaction_loops(ces_handle_t h, const double* Wsrc, bool accumulate_ssq, int first, int count) {
     const int64_t p = h->p, k = h->k, ld = h->ldJ;
     cudaStream_t st = h->st;
@@ -356,17 +363,24 @@ static int interaction_loops(ces_handle_t h, const double* Wsrc, bool accumulate
     const double invJ = 1.0 / (double)h->Jg;
     for (int64_t c0 = 0; c0 < h->Jl; c0 += h->panel) {
         const int64_t nc = (h->Jl - c0) < h->panel ? (h->Jl - c0) : h->panel;
-        for (int i = first; i < first + count; ++i) {
-            const int s = (h->rank + i) % h->nranks;
+        int i = first;
+        while (i < first + count) {
+            const int s0 = (h->rank + i) % h->nranks;
+            // run of positions with contiguous s (stops at the wrap-around); position 0 (own block) stays alone so
+            // that it can run while the gathers are in flight
+            int run = 1;
+            if (i > 0)
+                while (i + run < first + count && s0 + run < h->nranks) ++run;
             GemmCall g1;
             g1.a_mode = A_KM; g1.b_mode = B_KN;
             g1.M = (int)h->Jl; g1.N = (int)nc; g1.K = (int)k;
-            g1.A = e_block(h, s); g1.lda = ld;
+            g1.A = e_block(h, s0); g1.lda = ld;
             g1.B = Wsrc + c0; g1.ldb = ld;
             g1.C = h->D; g1.ldc = h->ldD;
             g1.alpha = invJ;
+            g1.batch = run; g1.a_batch_rows = k; g1.c_batch_elems = h->Jl * h->ldD;
             if (accumulate_ssq) {
-                const int tiles = gemm_tiles(g1.M, g1.N);
+                const int64_t tiles = (int64_t)gemm_tiles(g1.M, g1.N) * run;
                 if (npart + tiles > h->ssq_cap) return fail(CES_ERR_STATE, "phase3: partial-sum buffer too small%s", "");
                 g1.ssq_partials = h->ssq_partials + npart;
                 npart += tiles;
@@ -383,18 +397,23 @@ static int interaction_loops(ces_handle_t h, const double* Wsrc, bool accumulate
             if (h->profile) {
                 CES_CUDA(cudaEventRecord(h->ev_pool[h->ev_used + 1], st));
                 h->ev_used += 2;
-                h->prof_flops += 2.0 * (double)k * (double)g1.M * (double)g1.N;
+                h->prof_flops += 2.0 * (double)k * (double)g1.M * (double)g1.N * run;
             }
             GemmCall g2;
             g2.a_mode = A_MK; g2.b_mode = B_KN;
             g2.M = (int)p; g2.N = (int)nc; g2.K = (int)h->Jl;
-            g2.A = ut_block(h, s); g2.lda = ld;
+            g2.A = ut_block(h, s0); g2.lda = ld;
             g2.B = h->D; g2.ldb = h->ldD;
             g2.C = h->V + c0; g2.ldc = ld;
             g2.beta = (i == 0) ? 0.0 : 1.0;
-            // wave quantisation: d/128 x nc/128 tiles of a long contraction rarely fill 148 SMs evenly (e.g. 512 tiles
-            // = 3.46 waves); splitting the contraction 2-4 ways makes the tail negligible
-            {
+            if (run > 1) {
+                // per-block partial products into workspace planes, summed (+ beta * V) by the reduce kernel
+                if (!h->v_ws) CES_TRY(dalloc(h, &h->v_ws, h->v_ws_planes * p * h->panel));
+                g2.batch = run; g2.a_batch_rows = p; g2.b_batch_rows = h->Jl;
+                g2.splitk_ws = h->v_ws;
+            } else {
+                // wave quantisation: d/128 x nc/128 tiles of a long contraction rarely fill 148 SMs evenly (e.g. 512
+                // tiles = 3.46 waves); splitting the contraction 2-4 ways makes the tail negligible
                 const double tiles = (double)gemm_tiles(g2.M, g2.N);
                 int best = 1;
                 double best_eff = 0.0;
@@ -405,12 +424,13 @@ static int interaction_loops(ces_handle_t h, const double* Wsrc, bool accumulate
                     if (best_eff >= 0.97) break;
                 }
                 if (best > 1 && g2.K >= 64 * best) {
-                    if (!h->v_ws) CES_TRY(dalloc(h, &h->v_ws, 4 * p * h->panel));
+                    if (!h->v_ws) CES_TRY(dalloc(h, &h->v_ws, h->v_ws_planes * p * h->panel));
                     g2.splits = best;
                     g2.splitk_ws = h->v_ws;
                 }
             }
             CES_TRY(gemm(st, g2));
+            i += run;
         }
     }
     h->ssq_used = npart;

@@ -29,8 +29,9 @@ int gemm(cudaStream_t st, const GemmCall& c) {
     const int64_t nb = c.batch > 1 ? c.batch : 1;
     const int64_t a_rows = (c.a_mode == A_MK ? c.M : c.K) + (nb - 1) * c.a_batch_rows;
     const int64_t b_rows = (c.b_mode == B_NK ? c.N : c.K) + (nb - 1) * c.b_batch_rows;
-    if (nb > 1 && (c.splits > 1 || c.splitk_ws || c.ssq_partials))
-        return fail(CES_ERR_INVALID, "gemm: batching excludes split-K and sum-of-squares partials%s", "");
+    // a batch either writes one C per problem (c_batch_elems) or, with a workspace, is summed into a single C
+    // (one plane per batch, reduced like split-K); it cannot be combined with split-K itself
+    if (nb > 1 && c.splits > 1) return fail(CES_ERR_INVALID, "gemm: batching excludes split-K%s", "");
     if (c.a_mode == A_MK) CES_TRY(make_map_2d(&ma, c.A, c.K, a_rows, c.lda, 16, 128));
     else                  CES_TRY(make_map_2d(&ma, c.A, c.M, a_rows, c.lda, 16, 16));
     if (c.b_mode == B_NK) CES_TRY(make_map_2d(&mb, c.B, c.K, b_rows, c.ldb, 16, 128));
@@ -84,7 +85,7 @@ int gemm(cudaStream_t st, const GemmCall& c) {
         const long long total = (long long)c.M * c.N;
         const int threads = 256;
         splitk_reduce_kernel<<<(unsigned)ceil_div(total, threads), threads, 0, st>>>(
-            c.splitk_ws, a.splits, c.M, c.N, c.C, c.ldc, c.alpha, c.alpha_dev, c.beta, c.diag_add,
+            c.splitk_ws, nb > 1 ? (int)nb : a.splits, c.M, c.N, c.C, c.ldc, c.alpha, c.alpha_dev, c.beta, c.diag_add,
             (c.flags & GEMM_C_LOWER_ONLY) ? 1 : 0);
         CES_LAUNCHED(1);
     }

@@ -222,7 +222,8 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const int m_base = tm * GEMM_BM + wm * 64, n_base = tn * GEMM_BN + wn * 32;
     double ssq = 0.0;
     const bool to_ws = args.splitk_ws != nullptr;
-    double* out = to_ws ? args.splitk_ws + (size_t)blockIdx.z * (size_t)args.M * (size_t)args.N
+    // workspace planes: one per split (blockIdx.z) or, for a batch reduced into one C, one per batch (blockIdx.y)
+    double* out = to_ws ? args.splitk_ws + (size_t)(blockIdx.z + blockIdx.y) * (size_t)args.M * (size_t)args.N
                         : args.C + (size_t)blockIdx.y * (size_t)args.c_batch_elems;
     const long long ldo = to_ws ? (long long)args.N : args.ldc;
 #pragma unroll
@@ -256,7 +257,7 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             double tot = 0.0;
 #pragma unroll
             for (int w = 0; w < GEMM_CONSUMER_WARPS; ++w) tot += ssq_warp[w];
-            args.ssq_partials[blockIdx.x] = tot;
+            args.ssq_partials[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = tot;
         }
     }
 }

@@ -64,12 +64,14 @@ def _worker(rank, world, port, rule, d, k, J, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("rule,J", [("aldi", 301), ("aldi_constant", 256), ("eks", 130)])
-def test_two_gpu_step_matches_oracle(rule, J):
+@pytest.mark.parametrize("world,rule,J", [(2, "aldi", 301), (2, "aldi_constant", 256), (2, "eks", 130), (4, "aldi", 1030),
+                                          (4, "eks", 515), (3, "aldi_constant", 700)])
+def test_multi_gpu_step_matches_oracle(world, rule, J):
+    """world >= 3 exercises the batched launches over the other ranks' source blocks (rotated order with wrap-around)."""
     import torch.multiprocessing as mp
 
-    world = 2
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
