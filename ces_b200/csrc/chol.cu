@@ -43,14 +43,18 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A,
     __syncthreads();
     if (tid < nb) a[tid][tid] = dl[tid];
     __syncthreads();
-    // Inverse of the lower-triangular block: thread t owns column t of X = L^-1 (forward substitution;
-    // L[i][m] is a broadcast read, X[m][t] is conflict-free).
-    if (tid < nb) {
-        const int t = tid;
+    // Inverse of the lower-triangular block by forward substitution, column t of X = L^-1 owned by the four lanes
+    // 4t .. 4t+3 of one warp: they split the inner product over m, combine with two shuffles, lane 0 stores.
+    {
+        const int t = tid >> 2, part = tid & 3;
         for (int i = 0; i < nb; ++i) {
-            double s = (i == t) ? 1.0 : 0.0;
-            for (int m = 0; m < i; ++m) s -= a[i][m] * x[m][t];
-            x[i][t] = (i >= t) ? s / a[i][i] : 0.0;
+            double s = 0.0;
+            if (t < nb && i > t)
+                for (int m = t + part; m < i; m += 4) s -= a[i][m] * x[m][t];
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (part == 0 && t < nb) x[i][t] = (i > t) ? s / a[i][i] : (i == t ? 1.0 / a[i][i] : 0.0);
+            __syncwarp();
         }
     }
     __syncthreads();
