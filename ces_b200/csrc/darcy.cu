@@ -16,8 +16,12 @@
 //   T2 = p S2^T ; P_z = S2 T2_z             spline back to the centres (two more GEMMs)
 //   G[o, member] = P_z[obs_index[o]]        gather (or the transposed full field)
 #include <cooperative_groups.h>
+#include <cstdlib>
+#include <cstring>
+#include <type_traits>
 #include <vector>
 #include "kernels.h"
+#include "tma.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -223,6 +227,354 @@ darcy_pcg_kernel(const double* __restrict__ cn, double* __restrict__ pn, int K, 
     cluster.sync();              // no CTA may exit while a neighbour can still touch its shared memory
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Tiled solver (default).  Same system, same stopping rule, restated so that one SM carries 4 032 nodes instead of 2 016
+// and a reduction costs one DSMEM round trip instead of a cluster barrier:
+//
+//  * symmetric Jacobi scaling: with s = diag(A)^(-1/2) the solver runs plain CG on A^ = S A S (unit diagonal), which is
+//    Jacobi-preconditioned CG on A in exact arithmetic (same iterates, r^.r^ = r.M^-1 r, so the stopping rule
+//    r.M^-1 r <= tol^2 r0.M^-1 r0 is unchanged).  No z vector, no 1/diag array, 9 FP64 operations per node and iteration.
+//  * every thread owns a 4 x 2 tile of nodes: x, r, p and the 14 scaled weights of the faces inside / above / below the
+//    tile stay in registers; only p (for the neighbours) and the weights of the faces between horizontally adjacent tiles
+//    live in shared memory, stored as separate even-column / odd-column planes so every access is a conflict-free,
+//    fully coalesced 64-bit access.
+//  * cluster-wide sums and halo rows travel as st.async stores that complete a transaction count on the receiver's
+//    mbarrier (one DSMEM latency, no barrier.cluster, no L1 flush); the two barriers alternate (r.r / p.Ap), so a peer can
+//    run at most one synchronisation point ahead and single-buffered slots are race free.
+//  * the halo trick of the first kernel is kept: a CTA receives the neighbour's residual row and updates its own copy of
+//    the neighbour's p row with the same p = r + beta p, bit-identical to the owner's.
+struct TileShared {
+    double red[2][8];                   // [which][cluster rank] block partials of r.r (0) and p.Ap (1)
+    double wsum[2][16];                 // [which][warp] warp partials
+    unsigned long long bar[2];          // mbarriers of the two synchronisation points
+};
+
+__device__ __forceinline__ uint32_t cluster_map(uint32_t local_smem_addr, uint32_t rank) {
+    uint32_t out;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(out) : "r"(local_smem_addr), "r"(rank));
+    return out;
+}
+__device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uint32_t remote_bar) {
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr),
+                 "l"(__double_as_longlong(v)), "r"(remote_bar)
+                 : "memory");
+}
+__device__ __forceinline__ void st_async_f64x2(uint32_t remote_addr, double a, double b, uint32_t remote_bar) {
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(remote_addr),
+                 "l"(__double_as_longlong(a)), "l"(__double_as_longlong(b)), "r"(remote_bar)
+                 : "memory");
+}
+
+constexpr int TILE_THREADS = 512;
+
+// One cluster of C CTAs per member; CTA `crank` owns the interior rows 1 + crank*4G ... (4G rows, G row groups of 4);
+// thread (g, q) owns rows 4g..4g+3 of the strip and the columns 2q, 2q+1.  blockDim.x = round_up(G * KH, 32), KH = K/2
+// is a template parameter so every shared-memory access is one base register plus an immediate offset.
+template <int KH>
+__global__ void __launch_bounds__(TILE_THREADS, 1)
+darcy_pcg_tile_kernel(const double* __restrict__ cn, double* __restrict__ pn, int G, double tol2, int max_iter,
+                      int* __restrict__ iters_out) {
+    constexpr int K = 2 * KH;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks();
+    const int crank = (int)cluster.block_rank();
+    const long long member = blockIdx.x / C;
+    const int R = 4 * G;
+    extern __shared__ double smem[];
+    const int plane = (R + 2) * KH;
+    double* pe = smem;                  // (R+2) x KH  search direction, even columns, rows r0-1 .. r0+R
+    double* po = pe + plane;            //             odd columns
+    double* se = po + plane;            // (R+2) x KH  s = |diag|^(-1/2), even / odd columns (0 on boundary nodes)
+    double* so = se + plane;
+    double* we = so + plane;            // R x (KH+1)  entry q+1: -s_i s_j w of the face between columns 2q+1 and 2q+2; entry 0: 0
+    double* zh = we + R * (KH + 1);           // 2 x K       residual rows of the neighbouring strips: [0,K) above, [K,2K) below
+    __shared__ TileShared sh;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int g = tid / KH, q = tid - g * KH;
+    const bool active = g < G;
+    const int r0 = 1 + crank * R;
+    const int i0 = r0 + 4 * g;
+    const int lr = 4 * g + 1;           // local row of the tile's first row in the (R+2)-row planes
+    const double* cfield = cn + (size_t)member * K * K;
+
+    for (int idx = tid; idx < 4 * plane + R * (KH + 1); idx += blockDim.x) pe[idx] = 0.0;      // pe, po, se, so, we
+    for (int idx = tid; idx < 2 * K; idx += blockDim.x) zh[idx] = 0.0;
+    for (int idx = tid; idx < 48; idx += blockDim.x) (&sh.red[0][0])[idx] = 0.0;    // red + wsum
+    if (tid == 0) {
+        mbar_init(smem_u32(&sh.bar[0]), 1);
+        mbar_init(smem_u32(&sh.bar[1]), 1);
+        mbar_fence_init();
+    }
+    cluster.sync();
+
+    // ---- face weights from the nodal coefficients (solve_gwf.m:16-30): w = (c_i + c_j) / 2
+    unsigned negmask = 0;
+    double wv[5][2], wi[4], wr[4], s[4][2];       // wr and s are dead once the loop starts
+    {
+        double cl[6][4], wl[4];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            const int row = min(max(i0 - 1 + a, 0), K - 1);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int col = min(max(2 * q - 1 + b, 0), K - 1);
+                cl[a][b] = active ? __ldg(cfield + (size_t)row * K + col) : 0.0;
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 5; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) wv[a][b] = 0.5 * (cl[a][b + 1] + cl[a + 1][b + 1]);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            wl[a] = 0.5 * (cl[a + 1][0] + cl[a + 1][1]);
+            wi[a] = 0.5 * (cl[a + 1][1] + cl[a + 1][2]);
+            wr[a] = 0.5 * (cl[a + 1][2] + cl[a + 1][3]);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const int row = i0 + a, col = 2 * q + b;
+                const bool ok = active && row <= K - 2 && col >= 1 && col <= K - 2;
+                const double d = ((wv[a][b] + wv[a + 1][b]) + (b == 0 ? wl[a] : wi[a])) + (b == 0 ? wi[a] : wr[a]);
+                if (ok && d < 0.0) negmask |= 1u << (2 * a + b);
+                s[a][b] = ok ? 1.0 / sqrt(fabs(d)) : 0.0;
+            }
+        if (active) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                se[(lr + a) * KH + q] = s[a][0];
+                so[(lr + a) * KH + q] = s[a][1];
+            }
+            // s of the rows next to a strip boundary is needed by the neighbouring CTA for the shared faces
+            if (g == 0 && crank > 0) {
+                cluster.map_shared_rank(se, crank - 1)[(R + 1) * KH + q] = s[0][0];
+                cluster.map_shared_rank(so, crank - 1)[(R + 1) * KH + q] = s[0][1];
+            }
+            if (g == G - 1 && crank < C - 1) {
+                cluster.map_shared_rank(se, crank + 1)[q] = s[3][0];
+                cluster.map_shared_rank(so, crank + 1)[q] = s[3][1];
+            }
+        }
+    }
+    cluster.sync();
+
+    // ---- scaled, negated weights: nw = -(s_i s_j) w, identical on both sides of a face (the product s_i s_j commutes).
+    // s = 0 on boundary / padding nodes, so every face of such a node has weight 0: its A^p is exactly 0, its r and p stay
+    // 0 for ever, and no masking is needed inside the loop.
+    const int qw = q > 0 ? q - 1 : q, qe = q < KH - 1 ? q + 1 : q;
+    if (active) {
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const double* sp = b == 0 ? se : so;
+            wv[0][b] *= -(sp[(lr - 1) * KH + q] * s[0][b]);
+#pragma unroll
+            for (int a = 1; a < 4; ++a) wv[a][b] *= -(s[a - 1][b] * s[a][b]);
+            wv[4][b] *= -(s[3][b] * sp[(lr + 4) * KH + q]);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            wi[a] *= -(s[a][0] * s[a][1]);
+            we[(4 * g + a) * (KH + 1) + q + 1] = wr[a] * -(s[a][1] * se[(lr + a) * KH + qe]);
+        }
+    } else {
+#pragma unroll
+        for (int a = 0; a < 5; ++a) wv[a][0] = wv[a][1] = 0.0;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) wi[a] = 0.0;
+    }
+    // x = 0, r = b^ = s h^2, p = 0
+    double x[4][2], r[4][2], p[4][2];
+    const double h2 = 1.0 / ((double)(K - 1) * (double)(K - 1));
+    double part = 0.0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            x[a][b] = 0.0;
+            p[a][b] = 0.0;
+            r[a][b] = s[a][b] * h2;         // s = 0 on boundary nodes
+            if ((negmask >> (2 * a + b)) & 1u) r[a][b] = -r[a][b];
+            part += ((negmask >> (2 * a + b)) & 1u) ? -(r[a][b] * r[a][b]) : r[a][b] * r[a][b];
+        }
+    // A spline of exp(theta) can undershoot below zero (the reference's own example does: all 256 modes at prior scale
+    // 10), and then diag(A) has negative entries.  The reference hands the matrix to a direct solver; the first kernel ran
+    // CG with M = diag(A) regardless.  That recurrence is kept exactly: with s = |d|^(-1/2), sigma = sign(d) the scaled
+    // operator has diagonal sigma, the register `r` holds t = sigma r^ (so p = t + beta p), and r.M^-1 r = sum sigma t^2.
+    // The sign flips are integer operations compiled only into the variant a CTA with a negative diagonal runs.
+    const bool cta_signed = __syncthreads_or(negmask != 0) != 0;       // also: `we` is complete
+
+    // ---- synchronisation machinery
+    const uint32_t bar0 = smem_u32(&sh.bar[0]);         // bar[1] is bar0 + 8
+    const bool first_group = active && g == 0 && crank > 0, last_group = active && g == G - 1 && crank < C - 1;
+    uint32_t push_n_addr = 0, push_s_addr = 0;
+    if (first_group) push_n_addr = cluster_map(smem_u32(zh + K + 2 * q), crank - 1);    // our first row = its row below
+    if (last_group) push_s_addr = cluster_map(smem_u32(zh + 2 * q), crank + 1);         // our last row = its row above
+    const uint32_t push_n_bar = cluster_map(bar0, crank > 0 ? crank - 1 : 0), push_s_bar = cluster_map(bar0, crank < C - 1 ? crank + 1 : 0);
+    // bytes this CTA receives at each synchronisation point
+    const uint32_t expect0 = (uint32_t)((C - 1) * 8 + ((crank > 0) + (crank < C - 1)) * K * 8), expect1 = (uint32_t)((C - 1) * 8);
+    uint32_t phase = 0;                                 // bit w = parity to wait for on bar[w]
+    // lane l (1 <= l < C) of warp 0 sends this CTA's partial to the peer (crank + l) % C
+    uint32_t peer_slot0 = 0, peer_bar0 = 0;
+    if (wid == 0 && lane >= 1 && lane < C) {
+        const uint32_t peer = (uint32_t)((crank + lane) % C);
+        peer_slot0 = cluster_map(smem_u32(&sh.red[0][crank]), peer);        // red[1][crank] is 64 bytes further
+        peer_bar0 = cluster_map(bar0, peer);
+    }
+    auto push_rows = [&]() {
+        if (first_group) st_async_f64x2(push_n_addr, r[0][0], r[0][1], push_n_bar);
+        if (last_group) st_async_f64x2(push_s_addr, r[3][0], r[3][1], push_s_bar);
+    };
+    // part -> warp sum -> block sum -> every CTA of the cluster.  Every stage is a fixed xor-shuffle tree, identical in
+    // every warp of every CTA, so all threads of the cluster see bit-identical sums and take identical decisions.
+    auto reduce_send = [&](double v, int which) {
+        v = warp_sum(v);
+        if (lane == 0) sh.wsum[which][wid] = v;
+        __syncthreads();
+        if (C > 1) {
+            if (wid == 0) {
+                double b = sh.wsum[which][lane & 15];
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+                if (lane == 0) {
+                    sh.red[which][crank] = b;
+                    mbar_expect_tx(bar0 + 8 * which, which == 0 ? expect0 : expect1);
+                } else if (lane < C) {
+                    st_async_f64(peer_slot0 + 64 * which, b, peer_bar0 + 8 * which);
+                }
+            }
+        }
+    };
+    auto reduce_wait = [&](int which) -> double {
+        double b;
+        if (C > 1) {
+            mbar_wait(bar0 + 8 * which, (phase >> which) & 1u);
+            phase ^= 1u << which;
+            b = *(const volatile double*)&sh.red[which][lane & 7];
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+        } else {
+            b = *(const volatile double*)&sh.wsum[which][lane & 15];
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        return b;
+    };
+
+    // thread-constant shared-memory bases: everything in the loop is base + immediate
+    double* const pe_t = pe + lr * KH + q;              // own tile, row a: pe_t[a * KH]
+    double* const po_t = po + lr * KH + q;
+    const double* const we_t = we + 4 * g * (KH + 1) + q;   // [0]: west face of the tile, [1]: east face
+    const int dqw = qw - q, dqe = qe - q;               // -1 / +1, or 0 at the domain boundary (the face weight is 0 there)
+
+    push_rows();
+    reduce_send(part, 0);
+    double rr = reduce_wait(0);
+    const double rr0 = rr;
+    double beta = 0.0;
+    int it = 0;
+    auto flip = [&](double v, int node) -> double {          // sigma_node * v
+        return __hiloint2double(__double2hiint(v) ^ (int)(((negmask >> node) & 1u) << 31), __double2loint(v));
+    };
+    auto iterate = [&](auto tag) {
+        constexpr bool SIGNED = decltype(tag)::value;
+        for (it = 0; it < max_iter; ++it) {
+            // ---- p = r + beta p (own tile and this CTA's copies of the neighbouring rows)
+            if (active) {
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    p[a][0] = fma(beta, p[a][0], r[a][0]);
+                    p[a][1] = fma(beta, p[a][1], r[a][1]);
+                    pe_t[a * KH] = p[a][0];
+                    po_t[a * KH] = p[a][1];
+                }
+                if (first_group) {
+                    const double2 z = *reinterpret_cast<const double2*>(zh + 2 * q);
+                    pe[q] = fma(beta, pe[q], z.x);
+                    po[q] = fma(beta, po[q], z.y);
+                }
+                if (last_group) {
+                    const double2 z = *reinterpret_cast<const double2*>(zh + K + 2 * q);
+                    pe_t[4 * KH] = fma(beta, pe_t[4 * KH], z.x);
+                    po_t[4 * KH] = fma(beta, po_t[4 * KH], z.y);
+                }
+            }
+            __syncthreads();
+            // ---- ap = A^ p = sigma p + sum nw p_neighbour ; two accumulators for p.Ap
+            double ap[4][2];
+            double part0 = 0.0, part1 = 0.0;
+            if (active) {
+                const double n0 = pe_t[-KH], n1 = po_t[-KH];
+                const double s0 = pe_t[4 * KH], s1 = po_t[4 * KH];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const double pw = po_t[a * KH + dqw];
+                    const double pE = pe_t[a * KH + dqe];
+                    const double nwl = we_t[a * (KH + 1)], nwr = we_t[a * (KH + 1) + 1];
+                    const double up0 = a == 0 ? n0 : p[a - 1][0], up1 = a == 0 ? n1 : p[a - 1][1];
+                    const double dn0 = a == 3 ? s0 : p[a + 1][0], dn1 = a == 3 ? s1 : p[a + 1][1];
+                    double v0 = fma(wv[a][0], up0, SIGNED ? flip(p[a][0], 2 * a) : p[a][0]);
+                    double v1 = fma(wv[a][1], up1, SIGNED ? flip(p[a][1], 2 * a + 1) : p[a][1]);
+                    v0 = fma(wv[a + 1][0], dn0, v0);
+                    v1 = fma(wv[a + 1][1], dn1, v1);
+                    v0 = fma(nwl, pw, v0);
+                    v1 = fma(wi[a], p[a][0], v1);
+                    v0 = fma(wi[a], p[a][1], v0);
+                    v1 = fma(nwr, pE, v1);
+                    ap[a][0] = v0;
+                    ap[a][1] = v1;
+                    part0 = fma(p[a][0], v0, part0);
+                    part1 = fma(p[a][1], v1, part1);
+                }
+            } else {
+#pragma unroll
+                for (int a = 0; a < 4; ++a) ap[a][0] = ap[a][1] = 0.0;
+            }
+            reduce_send(part0 + part1, 1);
+            const double pap = reduce_wait(1);
+            const double alpha = rr / pap;
+            part0 = 0.0;
+            part1 = 0.0;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                r[a][0] = fma(-alpha, SIGNED ? flip(ap[a][0], 2 * a) : ap[a][0], r[a][0]);
+                r[a][1] = fma(-alpha, SIGNED ? flip(ap[a][1], 2 * a + 1) : ap[a][1], r[a][1]);
+                part0 = fma(SIGNED ? flip(r[a][0], 2 * a) : r[a][0], r[a][0], part0);
+                part1 = fma(SIGNED ? flip(r[a][1], 2 * a + 1) : r[a][1], r[a][1], part1);
+            }
+            push_rows();
+            reduce_send(part0 + part1, 0);
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) x[a][b] = fma(alpha, p[a][b], x[a][b]);     // overlaps the round trip
+            const double rr_new = reduce_wait(0);
+            if (rr_new <= tol2 * rr0) { ++it; break; }
+            beta = rr_new / rr;
+            rr = rr_new;
+        }
+    };
+    if (rr0 > 0.0) {
+        if (cta_signed) iterate(std::true_type{});
+        else iterate(std::false_type{});
+    }
+    // ---- nodal pressure = s * x^ (boundary stays zero: the buffer is cleared beforehand)
+    if (active) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int row = i0 + a;
+            if (row <= K - 2) {
+                double* out = pn + (size_t)member * K * K + (size_t)row * K + 2 * q;
+                *reinterpret_cast<double2*>(out) = make_double2(se[(lr + a) * KH + q] * x[a][0], so[(lr + a) * KH + q] * x[a][1]);
+            }
+        }
+    }
+    if (tid == 0 && crank == 0) atomicMax(iters_out, it);
+    cluster.sync();              // no CTA may exit while a neighbour can still touch its shared memory
+}
+
 // G[o, col0 + m] = P[m, obs[o]]  (n_obs rows) -- or, with obs == nullptr, the full transposed field.
 __global__ void __launch_bounds__(256) darcy_gather_kernel(const double* __restrict__ P, long long cells, int members,
                                                            const long long* __restrict__ obs, int rows,
@@ -236,6 +588,8 @@ __global__ void __launch_bounds__(256) darcy_gather_kernel(const double* __restr
 
 struct DarcyModel {
     int N = 0, p = 0, n_obs = 0, C = 1, R = 0;
+    int tile_C = 1, tile_G = 0;     // tiled solver: cluster size and row groups (of 4 rows) per CTA
+    bool legacy = false;            // CES_DARCY_KERNEL=legacy: the first (one quad per thread) solver, kept for A/B timing
     int64_t chunk = 0;
     cudaStream_t st = nullptr;
     double *PhiT = nullptr, *S = nullptr, *S2 = nullptr, *B0 = nullptr, *B1 = nullptr, *B2 = nullptr, *Upad = nullptr;
@@ -269,6 +623,37 @@ static int pcg_launch(DarcyModel* m, const double* cn, double* pn, int members, 
     return CES_OK;
 }
 
+static int pcg_tile_launch(DarcyModel* m, const double* cn, double* pn, int members, double tol, int max_iter) {
+    const int K = m->N, KH = K / 2, R = 4 * m->tile_G;
+    const size_t smem = ((size_t)4 * (R + 2) * KH + (size_t)R * (KH + 1) + 2 * K) * sizeof(double);
+    typedef void (*TileKernel)(const double*, double*, int, double, int, int*);
+    static const TileKernel table[8] = {darcy_pcg_tile_kernel<8>,  darcy_pcg_tile_kernel<16>, darcy_pcg_tile_kernel<24>,
+                                        darcy_pcg_tile_kernel<32>, darcy_pcg_tile_kernel<40>, darcy_pcg_tile_kernel<48>,
+                                        darcy_pcg_tile_kernel<56>, darcy_pcg_tile_kernel<64>};
+    static size_t configured[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int slot = K / 16 - 1;
+    const TileKernel kernel = table[slot];
+    if (smem > configured[slot]) {
+        CES_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[slot] = smem;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(members * m->tile_C));
+    cfg.blockDim = dim3((unsigned)round_up((int64_t)m->tile_G * KH, 32));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = m->st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)m->tile_C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CES_CUDA(cudaLaunchKernelEx(&cfg, kernel, cn, pn, m->tile_G, tol * tol, max_iter, m->iters));
+    CES_LAUNCHED(1);
+    return CES_OK;
+}
+
 }  // namespace ces
 
 using namespace ces;
@@ -294,6 +679,19 @@ int ces_darcy_create(int64_t N, int64_t p, const double* PhiT_host, const double
     m->C = C;
     m->R = (int)((N - 2 + C - 1) / C);
     if ((int64_t)m->R * quads > PCG_THREADS) { delete m; return fail(CES_ERR_INVALID, "ces_darcy_create: grid too large%s", ""); }
+    {   // tiled solver: NG row groups of 4 interior rows, G = ceil(NG / C) per CTA, G * N/2 threads <= TILE_THREADS
+        const int NG = (int)((N - 2 + 3) / 4), KH = (int)N / 2;
+        int tc = 1;
+        while (tc < 8 && ((NG + tc - 1) / tc) * KH > TILE_THREADS) tc *= 2;
+        if (const char* e = getenv("CES_DARCY_CLUSTER")) {          // experiments: a larger cluster than necessary
+            const int want = atoi(e);
+            if ((want == 1 || want == 2 || want == 4 || want == 8) && want >= tc && (want - 1) * ((NG + want - 1) / want) < NG)
+                tc = want;
+        }
+        m->tile_C = tc;
+        m->tile_G = (NG + tc - 1) / tc;
+        if (const char* e = getenv("CES_DARCY_KERNEL")) m->legacy = (strcmp(e, "legacy") == 0);
+    }
     const int64_t cells = N * N;
     m->chunk = (1ll << 29) / (cells * 8);          // 512 MiB per field buffer
     if (m->chunk > 32768) m->chunk = 32768;
@@ -389,7 +787,8 @@ int ces_darcy_forward(void* handle, const double* U, int64_t ldu, int64_t cols, 
         CES_TRY(gemm(st, cz));
         // 4. solve; nodal pressure into B0 (cleared: boundary nodes stay zero)
         CES_CUDA(cudaMemsetAsync(m->B0, 0, (size_t)mc * cells * sizeof(double), st));
-        CES_TRY(pcg_launch(m, m->B2, m->B0, (int)mc, tol, max_iter));
+        if (m->legacy) CES_TRY(pcg_launch(m, m->B2, m->B0, (int)mc, tol, max_iter));
+        else CES_TRY(pcg_tile_launch(m, m->B2, m->B0, (int)mc, tol, max_iter));
         // 5. back to the cell centres: T2 = p S2^T, P_z = S2 T2_z
         GemmCall t2 = t1;
         t2.A = m->B0; t2.B = m->S2; t2.C = m->B1;

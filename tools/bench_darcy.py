@@ -28,9 +28,11 @@ for (N, p, J, scale) in [(64, 64, 1024, 1.0), (64, 64, 1024, 10.0), (128, 256, 8
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 3
-    r = dict(N=N, p=p, J=J, prior_scale=scale, ms=ms, members_per_s=J / ms * 1e3, cg_iterations=m.last_iterations)
+    r = dict(kernel=os.environ.get('CES_DARCY_KERNEL', 'tile'), cluster=os.environ.get('CES_DARCY_CLUSTER', 'auto'),
+             N=N, p=p, J=J, prior_scale=scale, ms=ms, members_per_s=J / ms * 1e3, cg_iterations=m.last_iterations)
     print(r, flush=True)
     out.append(r)
     eng.close()
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(out, open("gpurun_out/bench_darcy.json", "w"), indent=1)
+tag = os.environ.get("CES_BENCH_TAG", "")
+json.dump(out, open("gpurun_out/bench_darcy%s.json" % tag, "w"), indent=1)
