@@ -23,7 +23,7 @@ EXPORTS = (
     "ces_version", "ces_last_error", "ces_create", "ces_destroy", "ces_set_problem", "ces_phase1_sums",
     "ces_phase2_centre", "ces_phase3_interact", "ces_phase4a_drift", "ces_phase4_update", "ces_step",
     "ces_step_host", "ces_forward_map", "ces_buffer", "ces_launch_count", "ces_gemm", "ces_potrf", "ces_posv",
-    "ces_profile_enable", "ces_profile_read", "ces_darcy_create", "ces_darcy_destroy", "ces_darcy_forward",
+    "ces_profile_enable", "ces_profile_read", "ces_darcy_create", "ces_darcy_destroy", "ces_darcy_forward", "ces_darcy_last_stats",
     "ces_peek_step_size", "ces_phase3b_cpp", "ces_phase3c_resolve", "ces_phase3f_products", "ces_phase3f_finish",
     "ces_fill_normal", "ces_phase3_blocks", "ces_frobenius",
 )
@@ -81,6 +81,7 @@ def load():
     lib.ces_darcy_create.argtypes = [_i64, _i64, _dp, _dp, _dp, _vp, _i64, _vp, ctypes.POINTER(_vp)]
     lib.ces_darcy_destroy.argtypes = [_vp]
     lib.ces_darcy_forward.argtypes = [_vp, _dp, _i64, _i64, _dp, _i64, _int, _dbl, _int, ctypes.POINTER(_int)]
+    lib.ces_darcy_last_stats.argtypes = [_vp, ctypes.POINTER(_i64), ctypes.POINTER(_i64), ctypes.POINTER(_dbl)]
     lib.ces_frobenius.argtypes = [_vp, _dp, _i64, _i64, _i64, ctypes.POINTER(_dbl)]
     lib.ces_fill_normal.argtypes = [_vp, ctypes.c_uint64, ctypes.c_uint64, _dp, _i64, _i64, _i64, _i64]
     lib.ces_gemm.argtypes = [_vp, _int, _int, _i64, _i64, _i64, _dbl, _dp, _i64, _dp, _i64, _dbl, _dp, _i64]

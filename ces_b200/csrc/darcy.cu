@@ -9,10 +9,9 @@
 //   Theta = U^T Phi^T                       DMMA GEMM (A_KM x B_KN)
 //   a     = exp(Theta)                      elementwise
 //   T1    = a S^T ; c_z = S T1_z            two DMMA GEMMs (stacked, then batched with the shared operand S)
-//   solve sum_faces w (p_i - p_nb) = h^2    darcy_pcg_kernel: Jacobi-preconditioned CG, the member's vectors live in
-//                                           registers + shared memory of a cluster of CTAs (row strips; halo rows are
-//                                           pushed into the neighbour's shared memory, dot products are combined through
-//                                           distributed shared memory)
+//   solve sum_faces w (p_i - p_nb) = h^2    darcy_pcg_tile_kernel: Jacobi-preconditioned CG, the member's vectors live in
+//                                           registers + shared memory of a cluster of CTAs (row strips; halo rows and
+//                                           partial dot products travel through distributed shared memory)
 //   T2 = p S2^T ; P_z = S2 T2_z             spline back to the centres (two more GEMMs)
 //   G[o, member] = P_z[obs_index[o]]        gather (or the transposed full field)
 #include <cooperative_groups.h>
@@ -27,209 +26,9 @@ namespace cg = cooperative_groups;
 
 namespace ces {
 
-constexpr int PCG_THREADS = 512;   // one quad of 4 adjacent nodes per thread
-
-// Shared-memory layout of one CTA: c and p strips with one halo row above and below.
-struct PcgShared {
-    double red[2][2][8];   // [parity][which dot][cta rank] partial dot products (read by every CTA of the cluster)
-};
-
-__device__ __forceinline__ double block_sum_512(double v, double* scratch) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    v = warp_sum(v);
-    __syncthreads();
-    if (lane == 0) scratch[wid] = v;
-    __syncthreads();
-    // every thread adds the 16 warp partials as the same balanced tree (depth 4 instead of a 16-long chain)
-    double v8[8];
-#pragma unroll
-    for (int w = 0; w < 8; ++w) v8[w] = scratch[2 * w] + scratch[2 * w + 1];
-    return ((v8[0] + v8[1]) + (v8[2] + v8[3])) + ((v8[4] + v8[5]) + (v8[6] + v8[7]));
-}
-
-// One cluster (gridDim.x = members * C, cluster dims (C,1,1)) solves one member.
-//   cn  : nodal coefficient fields, member-major (K x K each)
-//   pn  : nodal pressure out (K x K each, boundary rows/cols zero)
-__global__ void __launch_bounds__(PCG_THREADS, 1)
-darcy_pcg_kernel(const double* __restrict__ cn, double* __restrict__ pn, int K, int R, double tol2, int max_iter,
-                 int* __restrict__ iters_out) {
-    cg::cluster_group cluster = cg::this_cluster();
-    const int C = (int)cluster.num_blocks();
-    const int crank = (int)cluster.block_rank();
-    const long long member = blockIdx.x / C;
-    extern __shared__ double smem[];
-    double* cs = smem;                              // (R + 2) x K  nodal coefficients, rows r0-1 .. r0+R
-    double* ps = cs + (size_t)(R + 2) * K;          // (R + 2) x K  search direction with halos
-    double* zh = ps + (size_t)(R + 2) * K;          // 2 x K        z rows pushed by the neighbouring CTAs
-    __shared__ PcgShared sh;
-    __shared__ double scratch[PCG_THREADS / 32];
-
-    const int r0 = 1 + crank * R;                   // first interior nodal row of this strip
-    const int quads = K >> 2;
-    const int qrow = threadIdx.x / quads, qcol = threadIdx.x % quads;
-    const int i = r0 + qrow, j0 = qcol * 4;
-    const bool active = qrow < R;                   // threads beyond the strip only take part in the barriers
-    const bool row_ok = active && (i <= K - 2);
-    const double* cfield = cn + (size_t)member * K * K;
-
-    // ---- load coefficient strip (with halos) and clear p
-    for (int idx = threadIdx.x; idx < (R + 2) * K; idx += PCG_THREADS) {
-        const int rr = r0 - 1 + idx / K;
-        cs[idx] = (rr <= K - 1) ? cfield[(size_t)rr * K + idx % K] : 0.0;
-        ps[idx] = 0.0;
-    }
-    for (int idx = threadIdx.x; idx < 2 * K; idx += PCG_THREADS) zh[idx] = 0.0;
-    if (threadIdx.x < 32) (&sh.red[0][0][0])[threadIdx.x] = 0.0;
-    cluster.sync();                                 // zh is cleared everywhere before any neighbour pushes into it
-
-    // ---- per-node data in registers
-    double wN[4], wS[4], wWE[5], invd[4], x[4], r[4], p[4];
-    bool ok[4];
-    const double h2 = 1.0 / ((double)(K - 1) * (double)(K - 1));
-    {
-        const double* cm = cs + (size_t)((active ? qrow : 0) + 1) * K;     // own row
-        const double* cu = cm - K;                          // north
-        const double* cd = cm + K;                          // south
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int j = j0 + q;
-            ok[q] = row_ok && j >= 1 && j <= K - 2;
-            const double cc = row_ok ? cm[j] : 0.0;
-            wN[q] = row_ok ? 0.5 * (cu[j] + cc) : 0.0;
-            wS[q] = row_ok ? 0.5 * (cd[j] + cc) : 0.0;
-        }
-#pragma unroll
-        for (int q = 0; q < 5; ++q) {                       // face between columns j0+q-1 and j0+q
-            const int jl = j0 + q - 1, jr = j0 + q;
-            wWE[q] = (row_ok && jl >= 0 && jr <= K - 1) ? 0.5 * (cm[jl] + cm[jr]) : 0.0;
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const double d = wN[q] + wS[q] + wWE[q] + wWE[q + 1];
-            invd[q] = ok[q] ? 1.0 / d : 0.0;
-            x[q] = 0.0;
-            r[q] = ok[q] ? h2 : 0.0;                        // b - A*0
-        }
-    }
-    // z = M^-1 r ; p = z ; rz = r.z
-    double rz_loc = 0.0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) { p[q] = r[q] * invd[q]; rz_loc += r[q] * p[q]; }
-
-    double* prow = ps + (size_t)((active ? qrow : 0) + 1) * K + j0;
-    // Halo protocol (two cluster barriers per iteration instead of three): a CTA never sends p.  It pushes the first /
-    // last row of z = M^-1 r into the neighbour's `zh` rows right before the barrier of the r.z reduction, and after
-    // that barrier every CTA updates its own copy of the neighbour's p row with the same p = z + beta p the owner
-    // executes (bit-identical), so the search direction needs no exchange of its own.
-    double* zh_n = zh + j0;                 // z of the row above this strip (written by rank-1)
-    double* zh_s = zh + K + j0;             // z of the row below (written by rank+1)
-    double* push_n = (crank > 0) ? cluster.map_shared_rank(zh, crank - 1) + K + j0 : nullptr;   // our first row = its south halo
-    double* push_s = (crank < C - 1) ? cluster.map_shared_rank(zh, crank + 1) + j0 : nullptr;   // our last row = its north halo
-    const bool first_row = active && qrow == 0, last_row = active && qrow == R - 1;
-
-    auto push_z = [&](const double (&z)[4]) {
-        if (first_row && push_n) {
-            *reinterpret_cast<double2*>(push_n) = make_double2(z[0], z[1]);
-            *reinterpret_cast<double2*>(push_n + 2) = make_double2(z[2], z[3]);
-        }
-        if (last_row && push_s) {
-            *reinterpret_cast<double2*>(push_s) = make_double2(z[0], z[1]);
-            *reinterpret_cast<double2*>(push_s + 2) = make_double2(z[2], z[3]);
-        }
-    };
-    // Cluster-wide sum: every CTA pushes its block partial into slot [crank] of every CTA (remote stores are
-    // fire-and-forget), one cluster barrier, then each thread adds the C local slots in rank order -- the same
-    // order on every CTA, so all of them take identical decisions.
-    int parity = 0;
-    auto cluster_dot = [&](double local, int which) -> double {
-        const double b = block_sum_512(local, scratch);
-        if ((int)threadIdx.x < C) cluster.map_shared_rank(&sh, threadIdx.x)->red[parity][which][crank] = b;
-        cluster.sync();
-        // unused slots stay zero (static shared memory is not cleared: see the init below), fixed tree order
-        const double* rr = sh.red[parity][which];
-        return ((rr[0] + rr[1]) + (rr[2] + rr[3])) + ((rr[4] + rr[5]) + (rr[6] + rr[7]));
-    };
-
-    double z[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) z[q] = p[q];        // z0 = M^-1 r0 (computed above into p)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) p[q] = 0.0;
-    push_z(z);
-    double rz = cluster_dot(rz_loc, 0);     // the barrier inside also makes the z halos visible
-    parity ^= 1;
-    const double rz0 = rz;
-    double beta = 0.0;
-    int it = 0;
-    if (rz0 > 0.0) {
-        for (it = 0; it < max_iter; ++it) {
-            // ---- p = z + beta p: own quad, and this CTA's copies of the neighbouring rows
-            if (active) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) p[q] = z[q] + beta * p[q];
-                *reinterpret_cast<double2*>(prow) = make_double2(p[0], p[1]);
-                *reinterpret_cast<double2*>(prow + 2) = make_double2(p[2], p[3]);
-                if (first_row && crank > 0) {
-                    double* hp = prow - K;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) hp[q] = zh_n[q] + beta * hp[q];
-                }
-                if (last_row && crank < C - 1) {
-                    double* hp = prow + K;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) hp[q] = zh_s[q] + beta * hp[q];
-                }
-            }
-            __syncthreads();
-            // ---- ap = A p
-            double ap[4] = {0.0, 0.0, 0.0, 0.0}, pap_loc = 0.0;
-            if (active) {
-                const double2 n01 = *reinterpret_cast<const double2*>(prow - K), n23 = *reinterpret_cast<const double2*>(prow - K + 2);
-                const double2 s01 = *reinterpret_cast<const double2*>(prow + K), s23 = *reinterpret_cast<const double2*>(prow + K + 2);
-                const double pw = (j0 > 0) ? prow[-1] : 0.0;
-                const double pe = (j0 + 4 < K) ? prow[4] : 0.0;
-                const double pn_[4] = {n01.x, n01.y, n23.x, n23.y};
-                const double ps_[4] = {s01.x, s01.y, s23.x, s23.y};
-                const double pl[6] = {pw, p[0], p[1], p[2], p[3], pe};
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const double d = wN[q] + wS[q] + wWE[q] + wWE[q + 1];
-                    double v = d * p[q] - wN[q] * pn_[q] - wS[q] * ps_[q] - wWE[q] * pl[q] - wWE[q + 1] * pl[q + 2];
-                    ap[q] = ok[q] ? v : 0.0;
-                    pap_loc += p[q] * ap[q];
-                }
-            }
-            const double pap = cluster_dot(pap_loc, 0);
-            const double alpha = rz / pap;
-            double rz_new_loc = 0.0;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                x[q] += alpha * p[q];
-                r[q] -= alpha * ap[q];
-                z[q] = r[q] * invd[q];
-                rz_new_loc += r[q] * z[q];
-            }
-            push_z(z);
-            const double rz_new = cluster_dot(rz_new_loc, 1);
-            parity ^= 1;
-            if (rz_new <= tol2 * rz0) { ++it; break; }
-            beta = rz_new / rz;
-            rz = rz_new;
-        }
-    }
-    // ---- write the nodal pressure (boundary stays zero: the buffer is cleared beforehand)
-    if (row_ok) {
-        double* out = pn + (size_t)member * K * K + (size_t)i * K + j0;
-        *reinterpret_cast<double2*>(out) = make_double2(x[0], x[1]);
-        *reinterpret_cast<double2*>(out + 2) = make_double2(x[2], x[3]);
-    }
-    if (threadIdx.x == 0 && crank == 0) atomicMax(iters_out, it);
-    cluster.sync();              // no CTA may exit while a neighbour can still touch its shared memory
-}
-
 // ------------------------------------------------------------------------------------------------------------------
-// Tiled solver (default).  Same system, same stopping rule, restated so that one SM carries 4 032 nodes instead of 2 016
-// and a reduction costs one DSMEM round trip instead of a cluster barrier:
+// Conjugate-gradient solver.  Jacobi-preconditioned CG, restated so that one SM carries 4 032 nodes (everything but the
+// search direction in registers) and a cluster-wide reduction costs one DSMEM round trip instead of a cluster barrier:
 //
 //  * symmetric Jacobi scaling: with s = diag(A)^(-1/2) the solver runs plain CG on A^ = S A S (unit diagonal), which is
 //    Jacobi-preconditioned CG on A in exact arithmetic (same iterates, r^.r^ = r.M^-1 r, so the stopping rule
@@ -241,9 +40,9 @@ darcy_pcg_kernel(const double* __restrict__ cn, double* __restrict__ pn, int K, 
 //  * cluster-wide sums and halo rows travel as st.async stores that complete a transaction count on the receiver's
 //    mbarrier (one DSMEM latency, no barrier.cluster, no L1 flush); the two barriers alternate (r.r / p.Ap), so a peer can
 //    run at most one synchronisation point ahead and single-buffered slots are race free.
-//  * the halo trick of the first kernel is kept: a CTA receives the neighbour's residual row and updates its own copy of
+//  * a strip's halo needs no p exchange: a CTA receives the neighbour's residual row and updates its own copy of
 //    the neighbour's p row with the same p = r + beta p, bit-identical to the owner's.
-struct TileShared {
+struct __align__(16) TileShared {
     double red[2][8];                   // [which][cluster rank] block partials of r.r (0) and p.Ap (1)
     double wsum[2][16];                 // [which][warp] warp partials
     unsigned long long bar[2];          // mbarriers of the two synchronisation points
@@ -267,17 +66,29 @@ __device__ __forceinline__ void st_async_f64x2(uint32_t remote_addr, double a, d
 
 constexpr int TILE_THREADS = 512;
 
+// 1/x to (almost) full precision: MUFU.RCP64H seed + two Newton steps, 5 dependent operations instead of the ~20 of an
+// IEEE division.  Not correctly rounded (<= 2 ulp), which CG does not care about; what matters is that every thread of
+// the cluster executes the same instructions on the same bits and so gets the same alpha and beta.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
 // One cluster of C CTAs per member; CTA `crank` owns the interior rows 1 + crank*4G ... (4G rows, G row groups of 4);
 // thread (g, q) owns rows 4g..4g+3 of the strip and the columns 2q, 2q+1.  blockDim.x = round_up(G * KH, 32), KH = K/2
 // is a template parameter so every shared-memory access is one base register plus an immediate offset.
-template <int KH>
+template <int KH, bool CLUSTER>
 __global__ void __launch_bounds__(TILE_THREADS, 1)
 darcy_pcg_tile_kernel(const double* __restrict__ cn, double* __restrict__ pn, int G, double tol2, int max_iter,
                       int* __restrict__ iters_out) {
     constexpr int K = 2 * KH;
     cg::cluster_group cluster = cg::this_cluster();
-    const int C = (int)cluster.num_blocks();
-    const int crank = (int)cluster.block_rank();
+    const int C = CLUSTER ? (int)cluster.num_blocks() : 1;        // CLUSTER == false: one CTA per member, no DSMEM traffic
+    const int crank = CLUSTER ? (int)cluster.block_rank() : 0;
     const long long member = blockIdx.x / C;
     const int R = 4 * G;
     extern __shared__ double smem[];
@@ -306,7 +117,7 @@ darcy_pcg_tile_kernel(const double* __restrict__ cn, double* __restrict__ pn, in
         mbar_init(smem_u32(&sh.bar[1]), 1);
         mbar_fence_init();
     }
-    cluster.sync();
+    if (CLUSTER) cluster.sync(); else __syncthreads();
 
     // ---- face weights from the nodal coefficients (solve_gwf.m:16-30): w = (c_i + c_j) / 2
     unsigned negmask = 0;
@@ -359,7 +170,7 @@ darcy_pcg_tile_kernel(const double* __restrict__ cn, double* __restrict__ pn, in
             }
         }
     }
-    cluster.sync();
+    if (CLUSTER) cluster.sync(); else __syncthreads();
 
     // ---- scaled, negated weights: nw = -(s_i s_j) w, identical on both sides of a face (the product s_i s_j commutes).
     // s = 0 on boundary / padding nodes, so every face of such a node has weight 0: its A^p is exactly 0, its r and p stay
@@ -400,8 +211,8 @@ darcy_pcg_tile_kernel(const double* __restrict__ cn, double* __restrict__ pn, in
             part += ((negmask >> (2 * a + b)) & 1u) ? -(r[a][b] * r[a][b]) : r[a][b] * r[a][b];
         }
     // A spline of exp(theta) can undershoot below zero (the reference's own example does: all 256 modes at prior scale
-    // 10), and then diag(A) has negative entries.  The reference hands the matrix to a direct solver; the first kernel ran
-    // CG with M = diag(A) regardless.  That recurrence is kept exactly: with s = |d|^(-1/2), sigma = sign(d) the scaled
+    // 10), and then diag(A) has negative entries.  The reference hands the matrix to a direct solver; here the CG
+    // recurrence with M = diag(A) is run regardless, exactly as written for the unscaled system: with s = |d|^(-1/2), sigma = sign(d) the scaled
     // operator has diagonal sigma, the register `r` holds t = sigma r^ (so p = t + beta p), and r.M^-1 r = sum sigma t^2.
     // The sign flips are integer operations compiled only into the variant a CTA with a negative diagonal runs.
     const bool cta_signed = __syncthreads_or(negmask != 0) != 0;       // also: `we` is complete
@@ -410,7 +221,7 @@ darcy_pcg_tile_kernel(const double* __restrict__ cn, double* __restrict__ pn, in
     const uint32_t bar0 = smem_u32(&sh.bar[0]);         // bar[1] is bar0 + 8
     const bool first_group = active && g == 0 && crank > 0, last_group = active && g == G - 1 && crank < C - 1;
     uint32_t push_n_addr = 0, push_s_addr = 0;
-    if (first_group) push_n_addr = cluster_map(smem_u32(zh + K + 2 * q), crank - 1);    // our first row = its row below
+    if (first_group) push_n_addr = cluster_map(smem_u32(zh + K + 2 * q), (uint32_t)(crank > 0 ? crank - 1 : 0));    // our first row = its row below
     if (last_group) push_s_addr = cluster_map(smem_u32(zh + 2 * q), crank + 1);         // our last row = its row above
     const uint32_t push_n_bar = cluster_map(bar0, crank > 0 ? crank - 1 : 0), push_s_bar = cluster_map(bar0, crank < C - 1 ? crank + 1 : 0);
     // bytes this CTA receives at each synchronisation point
@@ -423,6 +234,14 @@ darcy_pcg_tile_kernel(const double* __restrict__ cn, double* __restrict__ pn, in
         peer_slot0 = cluster_map(smem_u32(&sh.red[0][crank]), peer);        // red[1][crank] is 64 bytes further
         peer_bar0 = cluster_map(bar0, peer);
     }
+    // broadcast loads of 16 doubles + a depth-4 tree: shorter than a shuffle tree, same order in every thread
+    auto sum16 = [&](const double* w) -> double {
+        const double2* w2 = reinterpret_cast<const double2*>(w);
+        double t[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const double2 v = w2[i]; t[i] = v.x + v.y; }
+        return ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
+    };
     auto push_rows = [&]() {
         if (first_group) st_async_f64x2(push_n_addr, r[0][0], r[0][1], push_n_bar);
         if (last_group) st_async_f64x2(push_s_addr, r[3][0], r[3][1], push_s_bar);
@@ -433,11 +252,9 @@ darcy_pcg_tile_kernel(const double* __restrict__ cn, double* __restrict__ pn, in
         v = warp_sum(v);
         if (lane == 0) sh.wsum[which][wid] = v;
         __syncthreads();
-        if (C > 1) {
+        if (CLUSTER) {
             if (wid == 0) {
-                double b = sh.wsum[which][lane & 15];
-#pragma unroll
-                for (int o = 8; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+                const double b = sum16(sh.wsum[which]);
                 if (lane == 0) {
                     sh.red[which][crank] = b;
                     mbar_expect_tx(bar0 + 8 * which, which == 0 ? expect0 : expect1);
@@ -448,19 +265,16 @@ darcy_pcg_tile_kernel(const double* __restrict__ cn, double* __restrict__ pn, in
         }
     };
     auto reduce_wait = [&](int which) -> double {
-        double b;
-        if (C > 1) {
+        if (CLUSTER) {
             mbar_wait(bar0 + 8 * which, (phase >> which) & 1u);
             phase ^= 1u << which;
-            b = *(const volatile double*)&sh.red[which][lane & 7];
-#pragma unroll
-            for (int o = 4; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
-        } else {
-            b = *(const volatile double*)&sh.wsum[which][lane & 15];
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+            const double2* rr2 = reinterpret_cast<const double2*>(sh.red[which]);      // unused slots stay zero
+            const double2 a = rr2[0], b = rr2[1];
+            if (C <= 4) return (a.x + a.y) + (b.x + b.y);
+            const double2 c = rr2[2], d = rr2[3];
+            return ((a.x + a.y) + (b.x + b.y)) + ((c.x + c.y) + (d.x + d.y));
         }
-        return b;
+        return sum16(sh.wsum[which]);
     };
 
     // thread-constant shared-memory bases: everything in the loop is base + immediate
@@ -480,6 +294,11 @@ darcy_pcg_tile_kernel(const double* __restrict__ cn, double* __restrict__ pn, in
     };
     auto iterate = [&](auto tag) {
         constexpr bool SIGNED = decltype(tag)::value;
+        double nwl[4] = {0.0, 0.0, 0.0, 0.0}, nwr[4] = {0.0, 0.0, 0.0, 0.0};
+        if (active) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) { nwl[a] = we_t[a * (KH + 1)]; nwr[a] = we_t[a * (KH + 1) + 1]; }
+        }
         for (it = 0; it < max_iter; ++it) {
             // ---- p = r + beta p (own tile and this CTA's copies of the neighbouring rows)
             if (active) {
@@ -504,7 +323,7 @@ darcy_pcg_tile_kernel(const double* __restrict__ cn, double* __restrict__ pn, in
             __syncthreads();
             // ---- ap = A^ p = sigma p + sum nw p_neighbour ; two accumulators for p.Ap
             double ap[4][2];
-            double part0 = 0.0, part1 = 0.0;
+            double part0 = 0.0, part1 = 0.0, part2 = 0.0, part3 = 0.0;
             if (active) {
                 const double n0 = pe_t[-KH], n1 = po_t[-KH];
                 const double s0 = pe_t[4 * KH], s1 = po_t[4 * KH];
@@ -512,47 +331,60 @@ darcy_pcg_tile_kernel(const double* __restrict__ cn, double* __restrict__ pn, in
                 for (int a = 0; a < 4; ++a) {
                     const double pw = po_t[a * KH + dqw];
                     const double pE = pe_t[a * KH + dqe];
-                    const double nwl = we_t[a * (KH + 1)], nwr = we_t[a * (KH + 1) + 1];
                     const double up0 = a == 0 ? n0 : p[a - 1][0], up1 = a == 0 ? n1 : p[a - 1][1];
                     const double dn0 = a == 3 ? s0 : p[a + 1][0], dn1 = a == 3 ? s1 : p[a + 1][1];
                     double v0 = fma(wv[a][0], up0, SIGNED ? flip(p[a][0], 2 * a) : p[a][0]);
                     double v1 = fma(wv[a][1], up1, SIGNED ? flip(p[a][1], 2 * a + 1) : p[a][1]);
                     v0 = fma(wv[a + 1][0], dn0, v0);
                     v1 = fma(wv[a + 1][1], dn1, v1);
-                    v0 = fma(nwl, pw, v0);
+                    v0 = fma(nwl[a], pw, v0);
                     v1 = fma(wi[a], p[a][0], v1);
                     v0 = fma(wi[a], p[a][1], v0);
-                    v1 = fma(nwr, pE, v1);
+                    v1 = fma(nwr[a], pE, v1);
                     ap[a][0] = v0;
                     ap[a][1] = v1;
-                    part0 = fma(p[a][0], v0, part0);
-                    part1 = fma(p[a][1], v1, part1);
+                    if (a & 1) {
+                        part2 = fma(p[a][0], v0, part2);
+                        part3 = fma(p[a][1], v1, part3);
+                    } else {
+                        part0 = fma(p[a][0], v0, part0);
+                        part1 = fma(p[a][1], v1, part1);
+                    }
                 }
             } else {
 #pragma unroll
                 for (int a = 0; a < 4; ++a) ap[a][0] = ap[a][1] = 0.0;
             }
-            reduce_send(part0 + part1, 1);
+            reduce_send((part0 + part1) + (part2 + part3), 1);
+            const double inv_rr = fast_rcp(rr);                 // for beta; off the critical path (overlaps the round trip)
             const double pap = reduce_wait(1);
-            const double alpha = rr / pap;
-            part0 = 0.0;
-            part1 = 0.0;
+            const double alpha = rr * fast_rcp(pap);
+            part0 = part1 = part2 = part3 = 0.0;
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
                 r[a][0] = fma(-alpha, SIGNED ? flip(ap[a][0], 2 * a) : ap[a][0], r[a][0]);
                 r[a][1] = fma(-alpha, SIGNED ? flip(ap[a][1], 2 * a + 1) : ap[a][1], r[a][1]);
-                part0 = fma(SIGNED ? flip(r[a][0], 2 * a) : r[a][0], r[a][0], part0);
-                part1 = fma(SIGNED ? flip(r[a][1], 2 * a + 1) : r[a][1], r[a][1], part1);
+                if (a & 1) {
+                    part2 = fma(SIGNED ? flip(r[a][0], 2 * a) : r[a][0], r[a][0], part2);
+                    part3 = fma(SIGNED ? flip(r[a][1], 2 * a + 1) : r[a][1], r[a][1], part3);
+                } else {
+                    part0 = fma(SIGNED ? flip(r[a][0], 2 * a) : r[a][0], r[a][0], part0);
+                    part1 = fma(SIGNED ? flip(r[a][1], 2 * a + 1) : r[a][1], r[a][1], part1);
+                }
             }
             push_rows();
-            reduce_send(part0 + part1, 0);
+            reduce_send((part0 + part1) + (part2 + part3), 0);
+            if (active) {           // next iteration's outer face weights: `ap` is dead, so this costs no registers
+#pragma unroll
+                for (int a = 0; a < 4; ++a) { nwl[a] = we_t[a * (KH + 1)]; nwr[a] = we_t[a * (KH + 1) + 1]; }
+            }
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
                 for (int b = 0; b < 2; ++b) x[a][b] = fma(alpha, p[a][b], x[a][b]);     // overlaps the round trip
             const double rr_new = reduce_wait(0);
             if (rr_new <= tol2 * rr0) { ++it; break; }
-            beta = rr_new / rr;
+            beta = rr_new * inv_rr;
             rr = rr_new;
         }
     };
@@ -571,8 +403,11 @@ darcy_pcg_tile_kernel(const double* __restrict__ cn, double* __restrict__ pn, in
             }
         }
     }
-    if (tid == 0 && crank == 0) atomicMax(iters_out, it);
-    cluster.sync();              // no CTA may exit while a neighbour can still touch its shared memory
+    if (tid == 0 && crank == 0) {
+        atomicMax(iters_out, it);
+        atomicAdd(iters_out + 1, it);           // total over the batch (statistics)
+    }
+    if (CLUSTER) cluster.sync();              // no CTA may exit while a neighbour can still touch its shared memory
 }
 
 // G[o, col0 + m] = P[m, obs[o]]  (n_obs rows) -- or, with obs == nullptr, the full transposed field.
@@ -587,51 +422,32 @@ __global__ void __launch_bounds__(256) darcy_gather_kernel(const double* __restr
 }
 
 struct DarcyModel {
-    int N = 0, p = 0, n_obs = 0, C = 1, R = 0;
-    int tile_C = 1, tile_G = 0;     // tiled solver: cluster size and row groups (of 4 rows) per CTA
-    bool legacy = false;            // CES_DARCY_KERNEL=legacy: the first (one quad per thread) solver, kept for A/B timing
+    int N = 0, p = 0, n_obs = 0;
+    int tile_C = 1, tile_G = 0;     // solver: cluster size and row groups (of 4 rows) per CTA
     int64_t chunk = 0;
     cudaStream_t st = nullptr;
     double *PhiT = nullptr, *S = nullptr, *S2 = nullptr, *B0 = nullptr, *B1 = nullptr, *B2 = nullptr, *Upad = nullptr;
     long long* obs = nullptr;
-    int* iters = nullptr;
+    int* iters = nullptr;           // [0] largest, [1] summed CG iteration count of the last forward call
+    std::vector<cudaEvent_t> ev;    // start/stop pairs around the solver launches of the last forward call
+    int ev_used = 0;
+    long long last_members = 0;
     int64_t upad_cols = 0;
 };
-
-static int pcg_launch(DarcyModel* m, const double* cn, double* pn, int members, double tol, int max_iter) {
-    const int K = m->N;
-    const size_t smem = ((size_t)2 * (m->R + 2) + 2) * K * sizeof(double);
-    static size_t configured = 0;
-    if (smem > configured) {
-        CES_CUDA(cudaFuncSetAttribute(darcy_pcg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(members * m->C));
-    cfg.blockDim = dim3(PCG_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = m->st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)m->C;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    CES_CUDA(cudaLaunchKernelEx(&cfg, darcy_pcg_kernel, cn, pn, K, m->R, tol * tol, max_iter, m->iters));
-    CES_LAUNCHED(1);
-    return CES_OK;
-}
 
 static int pcg_tile_launch(DarcyModel* m, const double* cn, double* pn, int members, double tol, int max_iter) {
     const int K = m->N, KH = K / 2, R = 4 * m->tile_G;
     const size_t smem = ((size_t)4 * (R + 2) * KH + (size_t)R * (KH + 1) + 2 * K) * sizeof(double);
     typedef void (*TileKernel)(const double*, double*, int, double, int, int*);
-    static const TileKernel table[8] = {darcy_pcg_tile_kernel<8>,  darcy_pcg_tile_kernel<16>, darcy_pcg_tile_kernel<24>,
-                                        darcy_pcg_tile_kernel<32>, darcy_pcg_tile_kernel<40>, darcy_pcg_tile_kernel<48>,
-                                        darcy_pcg_tile_kernel<56>, darcy_pcg_tile_kernel<64>};
-    static size_t configured[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const int slot = K / 16 - 1;
+    static const TileKernel table[16] = {
+        darcy_pcg_tile_kernel<8, false>,  darcy_pcg_tile_kernel<16, false>, darcy_pcg_tile_kernel<24, false>,
+        darcy_pcg_tile_kernel<32, false>, darcy_pcg_tile_kernel<40, false>, darcy_pcg_tile_kernel<48, false>,
+        darcy_pcg_tile_kernel<56, false>, darcy_pcg_tile_kernel<64, false>,
+        darcy_pcg_tile_kernel<8, true>,   darcy_pcg_tile_kernel<16, true>,  darcy_pcg_tile_kernel<24, true>,
+        darcy_pcg_tile_kernel<32, true>,  darcy_pcg_tile_kernel<40, true>,  darcy_pcg_tile_kernel<48, true>,
+        darcy_pcg_tile_kernel<56, true>,  darcy_pcg_tile_kernel<64, true>};
+    static size_t configured[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const int slot = K / 16 - 1 + (m->tile_C > 1 ? 8 : 0);
     const TileKernel kernel = table[slot];
     if (smem > configured[slot]) {
         CES_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -672,14 +488,7 @@ int ces_darcy_create(int64_t N, int64_t p, const double* PhiT_host, const double
     DarcyModel* m = new DarcyModel();
     m->N = (int)N; m->p = (int)p; m->n_obs = (int)n_obs;
     m->st = static_cast<cudaStream_t>(stream);
-    // strip height: one quad (4 nodes) per thread -> R * N/4 <= PCG_THREADS; cluster size from {1,2,4,8}
-    const int quads = (int)N / 4;
-    int C = 1;
-    while (C < 8 && ((N - 2 + C - 1) / C) * quads > PCG_THREADS) C *= 2;
-    m->C = C;
-    m->R = (int)((N - 2 + C - 1) / C);
-    if ((int64_t)m->R * quads > PCG_THREADS) { delete m; return fail(CES_ERR_INVALID, "ces_darcy_create: grid too large%s", ""); }
-    {   // tiled solver: NG row groups of 4 interior rows, G = ceil(NG / C) per CTA, G * N/2 threads <= TILE_THREADS
+    {   // NG row groups of 4 interior rows, G = ceil(NG / C) per CTA, G * N/2 threads <= TILE_THREADS
         const int NG = (int)((N - 2 + 3) / 4), KH = (int)N / 2;
         int tc = 1;
         while (tc < 8 && ((NG + tc - 1) / tc) * KH > TILE_THREADS) tc *= 2;
@@ -690,7 +499,6 @@ int ces_darcy_create(int64_t N, int64_t p, const double* PhiT_host, const double
         }
         m->tile_C = tc;
         m->tile_G = (NG + tc - 1) / tc;
-        if (const char* e = getenv("CES_DARCY_KERNEL")) m->legacy = (strcmp(e, "legacy") == 0);
     }
     const int64_t cells = N * N;
     m->chunk = (1ll << 29) / (cells * 8);          // 512 MiB per field buffer
@@ -709,7 +517,7 @@ int ces_darcy_create(int64_t N, int64_t p, const double* PhiT_host, const double
         else if (cudaMemcpyAsync(m->obs, obs_host, n_obs * sizeof(long long), cudaMemcpyHostToDevice, m->st) != cudaSuccess)
             s = fail(CES_ERR_CUDA, "obs upload failed%s", "");
     }
-    if (s == CES_OK && cudaMalloc(&m->iters, sizeof(int)) != cudaSuccess) s = fail(CES_ERR_NOMEM, "cudaMalloc failed%s", "");
+    if (s == CES_OK && cudaMalloc(&m->iters, 2 * sizeof(int)) != cudaSuccess) s = fail(CES_ERR_NOMEM, "cudaMalloc failed%s", "");
     if (s == CES_OK && cudaStreamSynchronize(m->st) != cudaSuccess) s = fail(CES_ERR_CUDA, "ces_darcy_create: upload failed%s", "");
     if (s != CES_OK) { ces_darcy_destroy(m); return s; }
     *out = m;
@@ -722,6 +530,7 @@ int ces_darcy_destroy(void* handle) {
     cudaStreamSynchronize(m->st);
     cudaFree(m->PhiT); cudaFree(m->S); cudaFree(m->S2); cudaFree(m->B0); cudaFree(m->B1); cudaFree(m->B2);
     cudaFree(m->Upad); cudaFree(m->obs); cudaFree(m->iters);
+    for (cudaEvent_t e : m->ev) cudaEventDestroy(e);
     delete m;
     cudaGetLastError();
     return CES_OK;
@@ -761,7 +570,9 @@ int ces_darcy_forward(void* handle, const double* U, int64_t ldu, int64_t cols, 
         CES_TRY(pad_copy(st, U, ldu, p, cols, m->Upad, ldp));
         Uuse = m->Upad; ldu_use = ldp;
     }
-    CES_CUDA(cudaMemsetAsync(m->iters, 0, sizeof(int), st));
+    CES_CUDA(cudaMemsetAsync(m->iters, 0, 2 * sizeof(int), st));
+    m->ev_used = 0;
+    m->last_members = cols;
     for (int64_t c0 = 0; c0 < cols; c0 += chunk) {
         const int64_t mc = (cols - c0) < chunk ? (cols - c0) : chunk;
         if (c0 % 2 != 0) return fail(CES_ERR_ALIGN, "ces_darcy_forward: odd chunk offset%s", "");
@@ -787,8 +598,15 @@ int ces_darcy_forward(void* handle, const double* U, int64_t ldu, int64_t cols, 
         CES_TRY(gemm(st, cz));
         // 4. solve; nodal pressure into B0 (cleared: boundary nodes stay zero)
         CES_CUDA(cudaMemsetAsync(m->B0, 0, (size_t)mc * cells * sizeof(double), st));
-        if (m->legacy) CES_TRY(pcg_launch(m, m->B2, m->B0, (int)mc, tol, max_iter));
-        else CES_TRY(pcg_tile_launch(m, m->B2, m->B0, (int)mc, tol, max_iter));
+        while ((int)m->ev.size() < m->ev_used + 2) {
+            cudaEvent_t e;
+            CES_CUDA(cudaEventCreate(&e));
+            m->ev.push_back(e);
+        }
+        CES_CUDA(cudaEventRecord(m->ev[m->ev_used], st));
+        CES_TRY(pcg_tile_launch(m, m->B2, m->B0, (int)mc, tol, max_iter));
+        CES_CUDA(cudaEventRecord(m->ev[m->ev_used + 1], st));
+        m->ev_used += 2;
         // 5. back to the cell centres: T2 = p S2^T, P_z = S2 T2_z
         GemmCall t2 = t1;
         t2.A = m->B0; t2.B = m->S2; t2.C = m->B1;
@@ -807,6 +625,24 @@ int ces_darcy_forward(void* handle, const double* U, int64_t ldu, int64_t cols, 
     CES_CUDA(cudaStreamSynchronize(st));
     if (iters_host) *iters_host = iters;
     if (iters >= max_iter) return fail(CES_ERR_STATE, "ces_darcy_forward: CG did not converge in %s%lld iterations", "", max_iter);
+    return CES_OK;
+}
+
+int ces_darcy_last_stats(void* handle, int64_t* members, int64_t* total_iterations, double* solver_ms) {
+    DarcyModel* m = static_cast<DarcyModel*>(handle);
+    if (!m) return fail(CES_ERR_INVALID, "ces_darcy_last_stats: null model%s", "");
+    int it[2] = {0, 0};
+    CES_CUDA(cudaStreamSynchronize(m->st));
+    CES_CUDA(cudaMemcpy(it, m->iters, 2 * sizeof(int), cudaMemcpyDeviceToHost));
+    double ms = 0.0;
+    for (int i = 0; i + 1 < m->ev_used; i += 2) {
+        float t = 0.f;
+        CES_CUDA(cudaEventElapsedTime(&t, m->ev[i], m->ev[i + 1]));
+        ms += t;
+    }
+    if (members) *members = m->last_members;
+    if (total_iterations) *total_iterations = it[1];
+    if (solver_ms) *solver_ms = ms;
     return CES_OK;
 }
 

@@ -188,6 +188,15 @@ class model(object):
         self.last_iterations = iters.value
         return G_dev
 
+    def last_stats(self):
+        """(members, CG iterations summed over the members, solver milliseconds) of the last device call."""
+        if self._dev is None:
+            return 0, 0, 0.0
+        members, total, ms = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_double()
+        _lib.check(_lib.load().ces_darcy_last_stats(self._dev[0], ctypes.byref(members), ctypes.byref(total),
+                                                    ctypes.byref(ms)))
+        return members.value, total.value, ms.value
+
     def solve_ensemble(self, U, full_solution=True):
         """Host convenience: U (p, n) numpy -> (N^2, n) cell-centre pressures or (n_obs, n) observations."""
         import torch

@@ -169,6 +169,9 @@ int ces_darcy_create(int64_t N, int64_t p, const double* PhiT_host, const double
 int ces_darcy_destroy(void* model);
 int ces_darcy_forward(void* model, const double* U_dev, int64_t ldu, int64_t cols, double* G_dev, int64_t ldg,
                       int full_solution, double tol, int max_iter, int* iters_host);
+/* Statistics of the last ces_darcy_forward call (measurement only, bench.py): members solved, CG iterations summed
+ * over the members, and the duration of the solver launches by CUDA events on the model's stream.  Synchronises. */
+int ces_darcy_last_stats(void* model, int64_t* members, int64_t* total_iterations, double* solver_ms);
 
 /* Frobenius norm of a device matrix (sampling.timestep_method(D, ...) for callers that own an explicit D). */
 int ces_frobenius(void* stream, const double* X_dev, int64_t ld, int64_t rows, int64_t cols, double* out_host);

@@ -1,5 +1,3 @@
-set -x
-timeout 600 python -m pytest tests/test_gpu_darcy.py -x -q -m gpu 2>&1 | tail -5
-CES_BENCH_TAG=_tile timeout 300 python tools/bench_darcy.py 2>&1 | tail -4
-CES_DARCY_CLUSTER=8 CES_BENCH_TAG=_tile_c8 timeout 300 python tools/bench_darcy.py 2>&1 | tail -4
-CES_DARCY_CLUSTER=2 CES_BENCH_TAG=_tile_c2 timeout 300 python tools/bench_darcy.py 2>&1 | tail -4
+timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -5
+timeout 600 python bench.py --workload cfg2 --steps 5 --warmup 3 > gpurun_out/bench_cfg2.json 2> gpurun_out/bench_cfg2.err; tail -c 1500 gpurun_out/bench_cfg2.json; tail -3 gpurun_out/bench_cfg2.err
+timeout 900 python bench.py --workload cfg4 --steps 2 --warmup 3 > gpurun_out/bench_cfg4_n1.json 2> gpurun_out/bench_cfg4_n1.err; tail -c 1500 gpurun_out/bench_cfg4_n1.json; tail -3 gpurun_out/bench_cfg4_n1.err
