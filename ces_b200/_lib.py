@@ -25,7 +25,7 @@ EXPORTS = (
     "ces_step_host", "ces_forward_map", "ces_buffer", "ces_launch_count", "ces_gemm", "ces_potrf", "ces_posv",
     "ces_profile_enable", "ces_profile_read", "ces_darcy_create", "ces_darcy_destroy", "ces_darcy_forward", "ces_darcy_last_stats",
     "ces_peek_step_size", "ces_phase3b_cpp", "ces_phase3c_resolve", "ces_phase3f_products", "ces_phase3f_finish",
-    "ces_fill_normal", "ces_phase3_blocks", "ces_frobenius",
+    "ces_fill_normal", "ces_phase3_blocks", "ces_frobenius", "ces_phase3d_spectral",
 )
 
 _i64, _int, _dbl, _vp = ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_void_p
@@ -66,6 +66,7 @@ def load():
     lib.ces_phase3f_products.argtypes = [_vp, _int]
     lib.ces_phase3f_finish.argtypes = [_vp, _int]
     lib.ces_phase3c_resolve.argtypes = [_vp, _int]
+    lib.ces_phase3d_spectral.argtypes = [_vp, ctypes.POINTER(_dbl), ctypes.POINTER(_int)]
     lib.ces_phase4a_drift.argtypes = [_vp, _dbl]
     lib.ces_phase4_update.argtypes = [_vp, _int, _int, _dbl, _dp, _i64, _dp, _i64, _dp, _i64,
                                       ctypes.POINTER(_dbl), ctypes.POINTER(_dbl)]

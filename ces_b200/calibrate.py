@@ -260,8 +260,9 @@ class sampling(enka):
         elif kind in ('constant', 'mix'):
             hk = const
         else:
-            raise NotImplementedError("time_step=%r: 'spectral' is outside the accelerated path and 'adaptive' "
-                                      "is undefined in the reference (ces/calibrate.py:255)" % (kind,))
+            raise NotImplementedError("time_step=%r with a caller-owned D: the update methods compute the spectral step "
+                                      "on the device from the ensemble (lambda_max(D) = lambda_max(Gamma^-1 C^pp)); "
+                                      "'adaptive' is undefined in the reference (ces/calibrate.py:255)" % (kind,))
         self._advance_time(hk)
         return hk
 
@@ -302,10 +303,12 @@ class sampling(enka):
             spun_up = not (len(t) == 0 or t[-1] < kwargs.get('spinup', 4.))
             resolve = ((t[-1] if len(t) else 0.0), 1.0) if rule == 'aldi' else None     # eks never re-solves for 'mix'
             return (const if spun_up else None), resolve
-        if kind in ('spectral', 'adaptive'):
+        if kind == 'spectral':
+            # hk = 1 / eigvals(D).real.max() (:249-251), no re-solve of D; aldi_constant never gets here (:519)
+            return None, 'spectral'
+        if kind == 'adaptive':
             raise NotImplementedError(
-                "time_step=%r: 'spectral' needs a non-symmetric J x J eigen-solve outside the accelerated path and "
-                "'adaptive' calls a method the reference does not define (ces/calibrate.py:250, 255)" % (kind,))
+                "time_step='adaptive' calls a method the reference does not define (ces/calibrate.py:255)")
         raise ValueError("unknown time_step %r" % (kind,))
 
     # ------------------------------------------------------------------ single updates on numpy arrays
@@ -322,6 +325,8 @@ class sampling(enka):
                                     switch=kwargs.get('switch', 1.), resolve=resolve,
                                     formulation=kwargs.get('formulation', getattr(self, 'formulation', 'interaction')))
         self._record(met, hk)
+        if resolve == 'spectral':
+            self.radspec.append(1. / hk)            # ces/calibrate.py:250
         return Uk
 
     def _draw_noise(self, shape, kwargs):
@@ -465,6 +470,8 @@ class sampling(enka):
                                           resolve=resolve,
                                           formulation=kwargs.get('formulation', getattr(self, 'formulation', 'interaction')))
                 self._record(met, hk)
+                if resolve == 'spectral':
+                    self.radspec.append(1. / hk)
             # an unknown ``update`` leaves the ensemble unchanged and records nothing, like :364-369 --
             # the reference then fails on the empty ``metrics['t']``; so do we
             if save_online:

@@ -35,7 +35,7 @@ struct ces_handle_s {
     int gram_splits = 1, p1_splits = 1;
     // K11 (time_step 'constant' / 'mix'): D re-solved with Gamma -> h*C^pp + Gamma
     std::vector<double> gamma_host;
-    double *GammaD = nullptr, *Cpp = nullptr, *Mk = nullptr, *MkLinv = nullptr, *MkInv = nullptr, *Wr = nullptr, *cpp_ws = nullptr;
+    double *GammaD = nullptr, *Cpp = nullptr, *Mk = nullptr, *MkLinv = nullptr, *MkInv = nullptr, *Wr = nullptr, *cpp_ws = nullptr, *eig_ws = nullptr;
     int cpp_splits = 1;
     // host staging
     double* hS = nullptr;   // pinned, S_COUNT doubles + 1 int
@@ -548,6 +548,18 @@ int ces_phase3c_resolve(ces_handle_t h, int rule) {
     CES_TRY(gemm(st, g));
     // the step size stays the one computed from the Gamma-only D (ces/calibrate.py:437 precedes :439-441)
     return interaction_loops(h, h->Wr, false, 0, h->nranks);
+}
+
+// time_step='spectral' (ces/calibrate.py:249-251): radspec = eigvals(D).real.max() = lambda_max(Gamma^-1 C^pp), see eig.cu.
+// Needs the (all-reduced) C^pp of ces_phase3b_cpp.
+int ces_phase3d_spectral(ces_handle_t h, double* radspec_host, int* lanczos_steps_host) {
+    CES_TRY(valid(h, true));
+    if (!h->Cpp) return fail(CES_ERR_STATE, "phase3d: ces_phase3b_cpp has not run%s", "");
+    const int64_t k = h->k;
+    const int64_t mmax = k < 384 ? k : 384;
+    if (!h->eig_ws) CES_TRY(dalloc(h, &h->eig_ws, (2 * (mmax + 1) + 2) * k + 4 * mmax + 8));
+    return spectral_radius(h->st, h->Cpp, h->ldk, k, h->gamma_diag ? nullptr : h->Ginv, h->gamma_diag ? h->ginv_diag : nullptr,
+                           h->eig_ws, mmax, radspec_host, lanczos_steps_host);
 }
 
 // ---- factored formulation: the same update without forming the J x J matrix -------------------------------------

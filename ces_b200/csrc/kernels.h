@@ -98,6 +98,10 @@ int spd_inverse_from_factor(cudaStream_t st, const double* L, int64_t ld, int64_
                             double* Ainv, int64_t ldo);
 int set_identity(cudaStream_t st, double* A, int64_t ld, int64_t n);
 
+// eig.cu -- lambda_max(Gamma^-1 C) by Lanczos in the Gamma^-1 inner product (time_step='spectral')
+int spectral_radius(cudaStream_t st, const double* C, int64_t ld, int64_t n, const double* Ginv, const double* ginv_diag,
+                    double* work, int64_t mmax, double* lambda_host, int* steps_host);
+
 // small.cu -- the whole update in one single-CTA kernel for small problems
 constexpr int SMALL_P_MAX = 8, SMALL_K_MAX = 16;
 struct SmallStepCall {

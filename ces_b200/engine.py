@@ -43,8 +43,9 @@ def run_phases(phases, buffer, comm, p, k, rule, resolve=None, formulation="inte
     all-reduces of "p1", "gram_e", "gram_w" instead of the all-gathers (opt-in).
 
     ``resolve``: None (default step size rule), "always" ('constant': D is formed once, with
-    hk C^pp + Gamma), or ``(t_last, threshold)`` ('mix': re-solve when t_last + hk > threshold,
-    ces/calibrate.py:470-473).  ``phases`` maps the names to callables, ``buffer(name)`` returns the torch
+    hk C^pp + Gamma), ``(t_last, threshold)`` ('mix': re-solve when t_last + hk > threshold,
+    ces/calibrate.py:470-473), or "spectral" (hk = 1 / lambda_max(D), :249-251: the "spectral" phase sets the
+    step size from the all-reduced C^pp and the update is called with the marker "spectral").  ``phases`` maps the names to callables, ``buffer(name)`` returns the torch
     tensor a collective runs on.  The engine passes the ctypes calls; tests/test_multirank_gloo.py passes a
     numpy stand-in to exercise this orchestration over gloo without a GPU."""
     if comm is not None:
@@ -103,6 +104,14 @@ def run_phases(phases, buffer, comm, p, k, rule, resolve=None, formulation="inte
     if comm is not None:
         allreduce_slice(buffer("scalars"), 0, 5)
     keep = False
+    if resolve == "spectral":
+        # hk = 1 / lambda_max(D) (ces/calibrate.py:249-251); lambda_max(D) = lambda_max(Gamma^-1 C^pp), see csrc/eig.cu
+        phases["cpp"]()
+        if comm is not None:
+            allreduce(buffer("cpp"))
+        phases["spectral"]()
+        phases["update"]("spectral")
+        return
     if resolve is not None:
         hk = phases["peek"]()
         if resolve == "always" or resolve[0] + hk > resolve[1]:
@@ -262,6 +271,20 @@ class Engine(object):
                 _lib.check(lib.ces_peek_step_size(h, ts, fh, ctypes.byref(hk)))
                 return hk.value
 
+            def spectral():
+                lam, steps = ctypes.c_double(), ctypes.c_int()
+                _lib.check(lib.ces_phase3d_spectral(h, ctypes.byref(lam), ctypes.byref(steps)))
+                self.last_radspec, self.last_lanczos_steps = lam.value, steps.value
+                return lam.value
+
+            def update(keep):
+                if keep == "spectral":
+                    kind, val = _lib.TS_FIXED, 1.0 / self.last_radspec
+                else:
+                    kind, val = (_lib.TS_KEEP if keep else ts), fh
+                _lib.check(lib.ces_phase4_update(h, r, kind, val, Up, ldu, Xp, ldx, Op, ldo, ctypes.byref(self._hk),
+                                                 self._met))
+
             phases = {
                 "sums": lambda: _lib.check(lib.ces_phase1_sums(h, Up, ldu, Gp, ldg)),
                 "centre": lambda: _lib.check(lib.ces_phase2_centre(h, r, Up, ldu, Gp, ldg)),
@@ -271,11 +294,11 @@ class Engine(object):
                 "peek": peek,
                 "cpp": lambda: _lib.check(lib.ces_phase3b_cpp(h)),
                 "resolve": lambda: _lib.check(lib.ces_phase3c_resolve(h, r)),
+                "spectral": spectral,
                 "products": lambda: _lib.check(lib.ces_phase3f_products(h, r)),
                 "finish_factored": lambda: _lib.check(lib.ces_phase3f_finish(h, r)),
                 "drift": lambda: _lib.check(lib.ces_phase4a_drift(h, float(switch))),
-                "update": lambda keep: _lib.check(lib.ces_phase4_update(
-                    h, r, _lib.TS_KEEP if keep else ts, fh, Up, ldu, Xp, ldx, Op, ldo, ctypes.byref(self._hk), self._met)),
+                "update": update,
             }
             comm = (self.dist, self.group, self.rank) if self.nranks > 1 else None
             run_phases(phases, self.buffer, comm, self.p, self.k, rule, resolve, formulation)

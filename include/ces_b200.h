@@ -113,6 +113,12 @@ int ces_phase3_blocks(ces_handle_t h, int rule, int first, int count);
 int ces_peek_step_size(ces_handle_t h, int ts_kind, double fixed_h, double* hk_host);
 int ces_phase3b_cpp(ces_handle_t h);
 int ces_phase3c_resolve(ces_handle_t h, int rule);
+/* time_step = 'spectral' (ces/calibrate.py:249-251: radspec = eigvals(D).real.max(), hk = 1 / radspec): after phase 3,
+ * ces_phase3b_cpp and the all-reduce of "cpp", ces_phase3d_spectral returns lambda_max(Gamma^-1 C^pp), which equals the
+ * largest eigenvalue of D (the non-zero spectrum of D = E^T (Gamma^-1 R / J) is that of Gamma^-1 R E^T / J = Gamma^-1 C^pp,
+ * real and non-negative), by Lanczos in the Gamma^-1 inner product with full re-orthogonalisation; *lanczos_steps
+ * receives the number of steps taken.  Phase 4 is then called with CES_TS_FIXED and 1 / radspec. */
+int ces_phase3d_spectral(ces_handle_t h, double* radspec_host, int* lanczos_steps_host);
 /* Factored formulation (opt-in; the same update to rounding without forming the J x J matrix):
  *   V = (1/J) (U~ E^T) W   and   ||D||_F^2 = sum((E E^T) o (W W^T)) / J^2.
  * ces_phase3f_products replaces phase 3: local parts of P1 = U~ E^T (d x k), GE = E E^T, GW = W W^T (k x k)

@@ -39,7 +39,7 @@ class NumpyPhases(object):
         self.buf["gram_w"] = torch.zeros(self.k, ldk, dtype=torch.float64)
         return {"sums": self.sums, "centre": self.centre, "interact": self.interact, "drift": self.drift,
                 "update": self.update, "peek": self.peek, "cpp": self.cpp, "resolve": self.resolve,
-                "products": self.products, "finish_factored": self.finish_factored}
+                "products": self.products, "finish_factored": self.finish_factored, "spectral": self.spectral}
 
     def sums(self):
         s = np.concatenate([self.G.sum(axis=1), self.U.sum(axis=1)])
@@ -117,6 +117,12 @@ class NumpyPhases(object):
         out = self.buf["cpp"].numpy()
         out[:] = 0.0
         out[:, :k] = (E @ E.T) / self.J
+
+    def spectral(self):
+        k = self.k
+        lam = np.linalg.eigvals(np.linalg.solve(self.Gamma, self.buf["cpp"].numpy()[:, :k])).real.max()
+        self.h_kept = 1.0 / lam
+        return lam
 
     def resolve(self):
         k = self.k

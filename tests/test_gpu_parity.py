@@ -93,6 +93,24 @@ def test_non_default_time_steps_match_oracle(d, k, J, dense):
             assert abs(s.metrics["t"][-1] - o["t"]) < TOL * o["t"], (rule, ts, t_hist)
 
 
+@pytest.mark.parametrize("d,k,J,dense", [(2, 10, 100, False), (6, 9, 40, True), (20, 33, 17, False), (64, 130, 600, True),
+                                         (64, 700, 2000, False), (16, 600, 900, True)])
+def test_spectral_time_step_matches_oracle(d, k, J, dense):
+    """time_step='spectral' (ces/calibrate.py:249-251): hk = 1 / eigvals(D).real.max().  The device never forms an
+    eigen-decomposition of the J x J matrix: lambda_max(D) = lambda_max(Gamma^-1 C^pp), found by Lanczos (csrc/eig.cu);
+    the oracle calls numpy's non-symmetric eigvals on D like the reference."""
+    pr = eo.linear_gaussian_problem(d, k, J, dense_gamma=dense)
+    for rule in ("aldi", "eks"):
+        s = _sampler(d, k, J, pr["mu"], pr["Sigma0"], pr["ustar"])
+        s._ensure_metrics()
+        Uk = getattr(s, METHOD[rule])(pr["y"], pr["U0"], pr["G"], pr["Gamma"], 0, time_step="spectral", xi=pr["xi"])
+        o = eo.step(rule, pr["y"], pr["U0"], pr["G"], pr["Gamma"], pr["mu"], pr["Sigma0"], pr["ustar"], pr["xi"],
+                    time_step="spectral")
+        assert abs(s.metrics["t"][-1] - o["hk"]) < TOL * o["hk"], rule
+        assert abs(s.radspec[-1] - 1.0 / o["hk"]) < TOL / o["hk"], rule
+        assert _rel(Uk, o["Uk"]) < TOL, rule
+
+
 @pytest.mark.parametrize("d,k,J,dense", [(2, 10, 100, False), (40, 30, 17, True), (64, 50, 1024, False), (130, 257, 1000, True),
                                          (1024, 10, 300, False)])
 def test_factored_formulation_matches_oracle(d, k, J, dense):

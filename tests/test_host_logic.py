@@ -38,9 +38,10 @@ def test_time_step_kwargs_map_to_step_options():
     """time_step semantics of ces/calibrate.py:247-260 (hk) and :439-441 / :470-473 (re-solve of D)."""
     s = calibrate.sampling(2, 3, 10)
     s.T = 30
-    for kind in ("spectral", "adaptive"):
-        with pytest.raises(NotImplementedError):
-            s._step_options("aldi", {"time_step": kind})
+    with pytest.raises(NotImplementedError):
+        s._step_options("aldi", {"time_step": "adaptive"})         # undefined in the reference (:255)
+    assert s._step_options("aldi", {"time_step": "spectral"}) == (None, "spectral")
+    assert s._step_options("aldi_constant", {"time_step": "spectral"}) == (None, None)
     with pytest.raises(ValueError):
         s._step_options("aldi", {"time_step": "bogus"})
     assert s._step_options("aldi", {}) == (None, None)

@@ -42,6 +42,8 @@ def _worker(rank, world, port, rule, d, k, J, q, ts=None, t_last=None, formulati
             fixed, resolve = 0.02, "always"
         elif ts == "mix":
             fixed, resolve = (0.02 if t_last >= 4.0 else None), (t_last, 1.0)
+        elif ts == "spectral":
+            resolve = "spectral"
         phases = ph.bind(rule, pr["U0"][:, sl], pr["G"][:, sl], pr["xi"][:, sl], fixed_h=fixed)
         run_phases(phases, ph.buffer, (dist, None, rank), d, k, rule, resolve, formulation)
         ref = eo.step(rule, pr["y"], pr["U0"], pr["G"], pr["Gamma"], pr["mu"], pr["Sigma0"], pr["ustar"], pr["xi"],
@@ -59,7 +61,7 @@ def _worker(rank, world, port, rule, d, k, J, q, ts=None, t_last=None, formulati
     (3, "aldi", 16, None, None), (2, "eki", 21, None, None),
     (2, "aldi", 29, "constant", 0.3), (2, "eks", 26, "constant", None), (2, "aldi", 31, "mix", 1.5),
     (2, "aldi", 31, "mix", 5.0), (2, "aldi", 35, "factored", None), (3, "eks", 22, "factored", None),
-    (2, "aldi_constant", 27, "factored", None)])
+    (2, "aldi_constant", 27, "factored", None), (2, "aldi", 30, "spectral", None), (3, "eks", 19, "spectral", None)])
 def test_sharded_orchestration_matches_single_process(world, rule, J, ts, t_last):
     formulation = "interaction"
     if ts == "factored":
