@@ -25,7 +25,8 @@ EXPORTS = (
     "ces_step_host", "ces_forward_map", "ces_buffer", "ces_launch_count", "ces_gemm", "ces_potrf", "ces_posv",
     "ces_profile_enable", "ces_profile_read", "ces_darcy_create", "ces_darcy_destroy", "ces_darcy_forward", "ces_darcy_last_stats",
     "ces_peek_step_size", "ces_phase3b_cpp", "ces_phase3c_resolve", "ces_phase3f_products", "ces_phase3f_finish",
-    "ces_fill_normal", "ces_phase3_blocks", "ces_frobenius", "ces_phase3d_spectral",
+    "ces_fill_normal", "ces_phase3_blocks", "ces_frobenius", "ces_phase3d_spectral", "ces_lorenz63_forward",
+    "ces_lorenz96_forward",
 )
 
 _i64, _int, _dbl, _vp = ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_void_p
@@ -82,6 +83,9 @@ def load():
     lib.ces_darcy_create.argtypes = [_i64, _i64, _dp, _dp, _dp, _vp, _i64, _vp, ctypes.POINTER(_vp)]
     lib.ces_darcy_destroy.argtypes = [_vp]
     lib.ces_darcy_forward.argtypes = [_vp, _dp, _i64, _i64, _dp, _i64, _int, _dbl, _int, ctypes.POINTER(_int)]
+    lib.ces_lorenz63_forward.argtypes = [_vp, _int, _dp, _i64, _i64, _i64, _dp, _i64, _i64, _dbl, _int, _i64, _dp, _i64, _dp, _i64, _dp, _i64]
+    lib.ces_lorenz96_forward.argtypes = [_vp, ctypes.POINTER(_int), _int, _int, _dp, _i64, _i64, _i64, _dp, _i64, _i64, _dbl,
+                                         _int, _i64, _i64, _int, _int, _dp, _i64, _dp, _i64, _dp, _i64]
     lib.ces_darcy_last_stats.argtypes = [_vp, ctypes.POINTER(_i64), ctypes.POINTER(_i64), ctypes.POINTER(_dbl)]
     lib.ces_frobenius.argtypes = [_vp, _dp, _i64, _i64, _i64, ctypes.POINTER(_dbl)]
     lib.ces_fill_normal.argtypes = [_vp, ctypes.c_uint64, ctypes.c_uint64, _dp, _i64, _i64, _i64, _i64]

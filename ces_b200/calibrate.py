@@ -15,7 +15,9 @@ ces/calibrate.py:404-416).  What differs is where the arithmetic runs:
   for the whole ensemble on the device; any other ``model.type == 'map'`` callable is
   evaluated particle by particle on the host exactly as ``enka.G_ens`` does
   (ces/calibrate.py:106-130) -- that is the user's model, not a fallback of ours.
-* ``model.type == 'pde'`` models (ODE integrators + statistics, ces/calibrate.py:132-168) keep the reference's host
+* ``model.type == 'pde'`` models (ODE integrators + statistics, ces/calibrate.py:132-168): the Lorenz models of
+  ``ces_b200.utils`` are integrated for the whole ensemble on the device (fixed-step RK4; statistics and the state
+  carry-over ``W0`` stay in HBM); any other 'pde' model keeps the reference's host
   protocol for the forward pass (``G_pde_ens``: the user's ``model.solve`` / ``model.statistics`` per particle, joblib
   when ``self.parallel``) with the state carry-over ``W0`` / ``ws`` / ``wt`` / ``update_wt`` semantics of ``run``; the
   update still runs on the device.
@@ -406,9 +408,37 @@ class sampling(enka):
         G_dev = torch.empty(self.n_obs, hi - lo, dtype=torch.float64, device=dev)
         known = rule in _RULE_METHOD
 
+        device_pde = is_pde and getattr(model, 'device_kind', None) is not None and hasattr(model, 'evaluate_ensemble_pde')
+        pde_state = {}
+
+        def forward_pde_device(U_dev, final):
+            """The same protocol with the ensemble integrated on the device (ces_b200.utils Lorenz models): statistics
+            into G_dev, final states into a device buffer that becomes the next W0 (:390-396) without touching the host;
+            the (n_obs + n_state, J) host array of the reference is assembled only when the trace or the result needs it."""
+            if 'W0' not in pde_state or ws_pool is not None:
+                pde_state['W0'] = torch.from_numpy(np.ascontiguousarray(self.W0[:, lo:hi])).to(dev)
+                pde_state['Wend'] = torch.empty_like(pde_state['W0'])
+            model.evaluate_ensemble_pde(eng, U_dev, pde_state['W0'], t_ode, G_dev, pde_state['Wend'])
+            G_full = None
+            if trace or final:
+                G_full = np.vstack([gather_host(G_dev, self.n_obs), gather_host(pde_state['Wend'], model.n_state)])
+            if kwargs.get('update_wt', True):
+                if ws_pool is not None:
+                    widx = np.random.randint(ws_pool.shape[0], size=self.J)
+                    if not final:
+                        self.Wall.append(widx)
+                    self.W0 = ws_pool[widx].T
+                else:
+                    pde_state['W0'], pde_state['Wend'] = pde_state['Wend'], pde_state['W0']
+                    if G_full is not None:
+                        self.W0 = np.copy(G_full[self.n_obs:, :])
+            return G_dev, G_full
+
         def forward_pde(U_dev, final):
             """Statistics + carried-over state (ces/calibrate.py:342-350, 390-396): the user's integrator on the host for
             this rank's particles; the full (n_obs + n_state, J) array is needed on every rank for the next W0."""
+            if device_pde:
+                return forward_pde_device(U_dev, final)
             U_loc = U_dev.cpu().numpy()
             G_loc = self.G_pde_ens(np.vstack([U_loc, self.W0[:, lo:hi]]), model, t_ode)
             if eng.nranks > 1:

@@ -179,6 +179,27 @@ int ces_darcy_forward(void* model, const double* U_dev, int64_t ldu, int64_t col
  * over the members, and the duration of the solver launches by CUDA events on the model's stream.  Synchronises. */
 int ces_darcy_last_stats(void* model, int64_t* members, int64_t* total_iterations, double* solver_ms);
 
+/* ---- batched 'pde'-type forward models (enka.G_pde_ens, ces/calibrate.py:132-168; ces/utils.py:124-447) --------------
+ * One call integrates every particle from its own initial condition W0[:, j] with the parameters U[:, j] over the
+ * uniform output grid t_i = i * dt_out, i < n_out, with `substeps` classical RK4 steps per output interval (the
+ * reference uses adaptive scipy integrators, one particle per Python call), accumulates the model's window statistics
+ * on the fly and returns them in G (n_obs x cols) and the final states in Wend (n_state x cols, may be NULL); traj
+ * (may be NULL) receives the sampled trajectory, sample i of state variable v of particle j at [(i * n_state + v) * ldt + j]
+ * (model.solve of a single particle).
+ * Lorenz 63 (ces/utils.py:124-229): p <= 2 parameters (r, b) -- or (log r, log b) when log_params != 0 --, sigma = 10;
+ *   G = means of (x, y, z, x^2, y^2, z^2, xy, xz, yz) over the last `window` samples of t[1:]  (:181-194).
+ * Lorenz 96 (ces/utils.py:231-447): state = n_slow slow then n_slow * n_fast fast variables; U row i sets parameter
+ *   param_slots[i] (0 h, 1 F, 2 log c, 3 b; defaults 1, 10, log 10, 10), which covers lorenz96 / Fc / Fb / hFb / hcb;
+ *   statistics (:332-342) over the last `window` samples after the first `skip` (= spinup * freq + 1): out_mode 0 ->
+ *   5 * n_slow rows; 1 -> their means over k (lorenz96_hom); 2 -> column out_col. */
+int ces_lorenz63_forward(void* stream, int log_params, const double* U_dev, int64_t ldu, int64_t p, int64_t cols,
+                         const double* W0_dev, int64_t ldw0, int64_t n_out, double dt_out, int substeps, int64_t window,
+                         double* G_dev, int64_t ldg, double* Wend_dev, int64_t ldwe, double* traj_dev, int64_t ldt);
+int ces_lorenz96_forward(void* stream, const int* param_slots, int n_slow, int n_fast, const double* U_dev, int64_t ldu,
+                         int64_t p, int64_t cols, const double* W0_dev, int64_t ldw0, int64_t n_out, double dt_out,
+                         int substeps, int64_t skip, int64_t window, int out_mode, int out_col, double* G_dev, int64_t ldg,
+                         double* Wend_dev, int64_t ldwe, double* traj_dev, int64_t ldt);
+
 /* Frobenius norm of a device matrix (sampling.timestep_method(D, ...) for callers that own an explicit D). */
 int ces_frobenius(void* stream, const double* X_dev, int64_t ld, int64_t rows, int64_t cols, double* out_host);
 

@@ -1,1 +1,1 @@
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "spectral or time_step" 2>&1 | tail -15
+timeout 900 python -m pytest tests/test_gpu_lorenz.py -x -q -m gpu 2>&1 | tail -30
