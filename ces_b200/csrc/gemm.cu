@@ -8,16 +8,23 @@ namespace ces {
 thread_local char g_last_error[512] = "";
 long long g_launches = 0;
 
-template <int AM, int BM_>
+template <int AM, int BM_, int ROWS>
 static int launch_one(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& a, dim3 grid) {
     static bool attr_set = false;
     if (!attr_set) {
-        CES_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<AM, BM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+        CES_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<AM, BM_, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
         attr_set = true;
     }
-    gemm_dmma_kernel<AM, BM_><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ma, mb, a);
+    gemm_dmma_kernel<AM, BM_, ROWS><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ma, mb, a);
     CES_LAUNCHED(1);
     return CES_OK;
+}
+template <int ROWS>
+static int launch_modes(cudaStream_t st, const GemmCall& c, const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& a, dim3 grid) {
+    if (c.a_mode == A_MK && c.b_mode == B_KN) return launch_one<0, 0, ROWS>(st, ma, mb, a, grid);
+    if (c.a_mode == A_KM && c.b_mode == B_KN) return launch_one<1, 0, ROWS>(st, ma, mb, a, grid);
+    if (c.a_mode == A_MK && c.b_mode == B_NK) return launch_one<0, 1, ROWS>(st, ma, mb, a, grid);
+    return launch_one<1, 1, ROWS>(st, ma, mb, a, grid);
 }
 
 int gemm_tiles(int M, int N) { return (int)(ceil_div(M, GEMM_BM) * ceil_div(N, GEMM_BN)); }
@@ -32,7 +39,9 @@ int gemm(cudaStream_t st, const GemmCall& c) {
     // a batch either writes one C per problem (c_batch_elems) or, with a workspace, is summed into a single C
     // (one plane per batch, reduced like split-K); it cannot be combined with split-K itself
     if (nb > 1 && c.splits > 1) return fail(CES_ERR_INVALID, "gemm: batching excludes split-K%s", "");
-    if (c.a_mode == A_MK) CES_TRY(make_map_2d(&ma, c.A, c.K, a_rows, c.lda, 16, 128));
+    // problems with at most 64 rows run the 64-row tile variant (half the A tile, no DMMA wasted on zero rows)
+    const int bm = (c.M <= 64 && nb == 1) ? 64 : GEMM_BM;
+    if (c.a_mode == A_MK) CES_TRY(make_map_2d(&ma, c.A, c.K, a_rows, c.lda, 16, bm));
     else                  CES_TRY(make_map_2d(&ma, c.A, c.M, a_rows, c.lda, 16, 16));
     if (c.b_mode == B_NK) CES_TRY(make_map_2d(&mb, c.B, c.K, b_rows, c.ldb, 16, 128));
     else                  CES_TRY(make_map_2d(&mb, c.B, c.N, b_rows, c.ldb, 16, 16));
@@ -42,7 +51,7 @@ int gemm(cudaStream_t st, const GemmCall& c) {
     a.C = c.C; a.ldc = c.ldc;
     a.alpha = c.alpha; a.beta = c.beta; a.alpha_dev = c.alpha_dev;
     a.ssq_partials = c.ssq_partials;
-    a.tiles_m = (int)ceil_div(c.M, GEMM_BM);
+    a.tiles_m = (int)ceil_div(c.M, bm);
     a.tiles_n = (int)ceil_div(c.N, GEMM_BN);
     static const int env_group = []() { const char* e = std::getenv("CES_GEMM_GROUP_M"); return e ? atoi(e) : 0; }();
     a.group_m = c.group_m > 0 ? c.group_m : (env_group > 0 ? env_group : 16);
@@ -75,12 +84,7 @@ int gemm(cudaStream_t st, const GemmCall& c) {
     a.splits = (int)ceil_div(kb_total, a.kblocks_per_split);
     a.splitk_ws = c.splitk_ws;
     dim3 grid((unsigned)(a.tiles_m * a.tiles_n), (unsigned)nb, (unsigned)a.splits);
-    int s;
-    if (c.a_mode == A_MK && c.b_mode == B_KN) s = launch_one<0, 0>(st, ma, mb, a, grid);
-    else if (c.a_mode == A_KM && c.b_mode == B_KN) s = launch_one<1, 0>(st, ma, mb, a, grid);
-    else if (c.a_mode == A_MK && c.b_mode == B_NK) s = launch_one<0, 1>(st, ma, mb, a, grid);
-    else s = launch_one<1, 1>(st, ma, mb, a, grid);
-    CES_TRY(s);
+    CES_TRY(bm == 64 ? launch_modes<64>(st, c, ma, mb, a, grid) : launch_modes<128>(st, c, ma, mb, a, grid));
     if (via_ws) {
         const long long total = (long long)c.M * c.N;
         const int threads = 256;

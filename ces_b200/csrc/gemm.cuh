@@ -76,7 +76,9 @@ __device__ __forceinline__ double lds64(uint32_t addr) {
     return v;
 }
 
-template <int A_MODE /*0=MK,1=KM*/, int B_MODE /*0=KN,1=NK*/>
+// BM = 128: the 8 consumer warps form a 2 x 4 grid of 64 x 32 outputs.  BM = 64 (problems with at most 64 rows: V = U~ D,
+// C Z, L xi at d <= 64 would waste half of every DMMA on zero rows): a 1 x 8 grid of 64 x 16 outputs, half the A tile.
+template <int A_MODE /*0=MK,1=KM*/, int B_MODE /*0=KN,1=NK*/, int BM /*128 or 64*/>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmArgs args) {
     extern __shared__ uint8_t smem_raw[];
@@ -102,7 +104,7 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
     // ---- contraction range of this CTA
     int kb_total = (args.K + GEMM_BK - 1) / GEMM_BK;
-    if (args.flags & GEMM_A_LOWER_TRI) kb_total = min(kb_total, ((tm + 1) * GEMM_BM + GEMM_BK - 1) / GEMM_BK);
+    if (args.flags & GEMM_A_LOWER_TRI) kb_total = min(kb_total, ((tm + 1) * BM + GEMM_BK - 1) / GEMM_BK);
     if (args.flags & GEMM_B_UPPER_TRI) kb_total = min(kb_total, ((tn + 1) * GEMM_BN + GEMM_BK - 1) / GEMM_BK);
     int kb_begin = 0, kb_end = kb_total;
     if (args.splits > 1) {
@@ -133,13 +135,14 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         if (warp == GEMM_CONSUMER_WARPS && lane == 0) {
             tma_prefetch_desc(&mapA);
             tma_prefetch_desc(&mapB);
-            const int m0 = tm * GEMM_BM, n0 = tn * GEMM_BN;
+            const int m0 = tm * BM, n0 = tn * GEMM_BN;
+            constexpr uint32_t stage_tx = (uint32_t)(BM * GEMM_BK * 8 + GEMM_TILE_BYTES);
             for (int it = 0; it < nkb; ++it) {
                 const int s = it % GEMM_STAGES;
                 const uint32_t ph = (uint32_t)(it / GEMM_STAGES) & 1u;
                 mbar_wait(empty0 + 8 * s, ph ^ 1u);
                 const uint32_t fb = full0 + 8 * s;
-                mbar_expect_tx(fb, GEMM_STAGE_BYTES);
+                mbar_expect_tx(fb, stage_tx);
                 const uint32_t a_dst = smem_base + s * GEMM_STAGE_BYTES;
                 const uint32_t b_dst = a_dst + GEMM_TILE_BYTES;
                 const int k0 = (reverse_k ? (kb_end - 1 - it) : (kb_begin + it)) * GEMM_BK;
@@ -148,7 +151,7 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     tma_load_2d(a_dst, &mapA, fb, k0, m0 + az);
                 } else {
 #pragma unroll
-                    for (int o = 0; o < 8; ++o) tma_load_2d(a_dst + o * 2048, &mapA, fb, m0 + 16 * o, k0 + az);
+                    for (int o = 0; o < BM / 16; ++o) tma_load_2d(a_dst + o * 2048, &mapA, fb, m0 + 16 * o, k0 + az);
                 }
                 if (B_MODE == 1) {
                     tma_load_2d(b_dst, &mapB, fb, k0, n0 + bz);
@@ -163,14 +166,15 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
     // ================================ DMMA consumers ================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(GEMM_REGS_CONSUMER));
-    const int wm = warp >> 2, wn = warp & 3;   // 2 x 4 warps, 64 x 32 outputs each
+    constexpr int NJ = BM == 128 ? 4 : 2;                               // 8-column blocks per warp
+    const int wm = BM == 128 ? warp >> 2 : 0, wn = BM == 128 ? (warp & 3) : warp;
     const int g = lane >> 2, t = lane & 3;
 
-    double acc[8][4][2];
+    double acc[8][NJ][2];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     // Per-lane byte offsets of the step-0 fragments of 8x8 blocks 0 and 1 inside a stage.  Block i
     // sits 2048*(i>>1) bytes further in both tile layouts (an LDS immediate), and step `st` changes
@@ -179,7 +183,7 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         a_par[q] = (A_MODE == 0) ? off_kc(wm * 64 + perm_kc(q, g), t) : off_mc(wm * 64 + perm_mc(q, g), t);
-        b_par[q] = GEMM_TILE_BYTES + ((B_MODE == 1) ? off_kc(wn * 32 + perm_kc(q, g), t) : off_mc(wn * 32 + perm_mc(q, g), t));
+        b_par[q] = GEMM_TILE_BYTES + ((B_MODE == 1) ? off_kc(wn * (8 * NJ) + perm_kc(q, g), t) : off_mc(wn * (8 * NJ) + perm_mc(q, g), t));
     }
 
     for (int it = 0; it < nkb; ++it) {
@@ -199,17 +203,17 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 pb[q] = sb + ((B_MODE == 1) ? (b_par[q] ^ (uint32_t)(st << 5))
                                             : ((b_par[q] ^ (uint32_t)((st & 1) << 6)) + (uint32_t)(st * 512)));
             }
-            double a[8], b[4];
+            double a[8], b[NJ];
             a[0] = lds64<0>(pa[0]);    a[1] = lds64<0>(pa[1]);
             a[2] = lds64<2048>(pa[0]); a[3] = lds64<2048>(pa[1]);
             a[4] = lds64<4096>(pa[0]); a[5] = lds64<4096>(pa[1]);
             a[6] = lds64<6144>(pa[0]); a[7] = lds64<6144>(pa[1]);
             b[0] = lds64<0>(pb[0]);    b[1] = lds64<0>(pb[1]);
-            b[2] = lds64<2048>(pb[0]); b[3] = lds64<2048>(pb[1]);
+            if (NJ == 4) { b[NJ - 2] = lds64<2048>(pb[0]); b[NJ - 1] = lds64<2048>(pb[1]); }
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty0 + 8 * s);
@@ -219,7 +223,7 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     double alpha = args.alpha;
     if (args.alpha_dev) alpha *= *args.alpha_dev;
     const double beta = args.beta;
-    const int m_base = tm * GEMM_BM + wm * 64, n_base = tn * GEMM_BN + wn * 32;
+    const int m_base = tm * BM + wm * 64, n_base = tn * GEMM_BN + wn * (8 * NJ);
     double ssq = 0.0;
     const bool to_ws = args.splitk_ws != nullptr;
     // workspace planes: one per split (blockIdx.z) or, for a batch reduced into one C, one per batch (blockIdx.y)
@@ -232,7 +236,7 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         if (m >= args.M) continue;
         double* row = out + (size_t)m * ldo;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < NJ; ++j) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int n = n_base + ((B_MODE == 1) ? perm_kc(j, 2 * t + e) : perm_mc(j, 2 * t + e));

@@ -37,6 +37,8 @@ def main():
               (16384, 64, 256), (65536, 64, 256), (262144, 64, 256), (16384, 4096, 16384), (65536, 4096, 16384)]
     if "--quick" not in sys.argv:
         shapes.append((262144, 1024, 4096))
+    if os.environ.get("CES_SWEEP_SHAPES"):           # "J,d,k;J,d,k"
+        shapes = [tuple(int(v) for v in item.split(",")) for item in os.environ["CES_SWEEP_SHAPES"].split(";")]
     out = []
     for (J, d, k) in shapes:
         lo, hi = shard_range(J, rank, world)
