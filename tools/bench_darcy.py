@@ -40,7 +40,8 @@ for (N, p, J, scale) in SHAPES:
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 3
-    r = dict(cluster=os.environ.get('CES_DARCY_CLUSTER', 'auto'),
+    members_, total_its_, solver_ms_ = m.last_stats()
+    r = dict(mean_iterations=total_its_ / max(members_, 1), solver_ms=solver_ms_, cluster=os.environ.get('CES_DARCY_CLUSTER', 'auto'),
              N=N, p=p, J=J, prior_scale=scale, ms=ms, members_per_s=J / ms * 1e3, cg_iterations=m.last_iterations)
     print(r, flush=True)
     out.append(r)
