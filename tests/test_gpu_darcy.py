@@ -16,7 +16,8 @@ def _rel(a, b):
 
 
 @pytest.mark.parametrize("N,p,members,scale", [(16, 10, 7, 1.0), (16, 10, 5, 10.0), (32, 24, 4, 3.0), (64, 64, 4, 1.0),
-                                               (64, 64, 3, 10.0), (128, 256, 2, 1.0)])
+                                               (64, 64, 3, 10.0), (128, 256, 2, 1.0), (48, 30, 3, 2.0), (80, 40, 2, 1.0),
+                                               (96, 64, 2, 1.0), (112, 64, 2, 3.0)])
 def test_truncated_model_matches_oracle(N, p, members, scale):
     rng = np.random.default_rng(N + p)
     U = scale * rng.standard_normal((p, members))
