@@ -345,7 +345,10 @@ darcy_pcg_tile_kernel(const double* __restrict__ cn, double* __restrict__ pn, in
             __syncthreads();
             // in-place Gauss-Jordan without pivoting (Ac is symmetric positive definite, condition number O(30)).  Every
             // thread keeps its JP elements of one row in registers; the pivot row and pivot column of the next step are
-            // published through double-buffered shared memory, so a step costs one barrier.
+            // published through double-buffered shared memory, so a step costs one barrier.  A step is one uniform
+            // rank-one update e -= f * (row_k[j] / piv): publishing piv + 1 as the pivot row's own diagonal entry and
+            // using f = piv - 1 for the pivot row itself produces 1/piv, row_k/piv and -col_k/piv in the right places
+            // without any per-element case distinction.
             double* prowB = prow;                       // [2][64], permuted like rcv
             double* fcolB = prow + 128;                 // [2][64]
             const bool worker = tid < 64 * PARTS;
@@ -353,10 +356,16 @@ darcy_pcg_tile_kernel(const double* __restrict__ cn, double* __restrict__ pn, in
             double el[JP];
 #pragma unroll
             for (int jj = 0; jj < JP; ++jj) el[jj] = worker ? Ainv[jj * (64 * PARTS) + tid] : 0.0;
+            auto pick = [&](int idx) -> double {         // el[idx] for a warp-uniform run-time index
+                double v = el[0];
+#pragma unroll
+                for (int jj = 1; jj < JP; ++jj) v = (jj == idx) ? el[jj] : v;
+                return v;
+            };
             if (worker) {
                 if (gi == 0) {
 #pragma unroll
-                    for (int jj = 0; jj < JP; ++jj) prowB[jj * PARTS + gp] = el[jj];
+                    for (int jj = 0; jj < JP; ++jj) prowB[jj * PARTS + gp] = el[jj] + ((gp == 0 && jj == 0) ? 1.0 : 0.0);
                 }
                 if (gp == 0) fcolB[gi] = el[0];
             }
@@ -368,23 +377,18 @@ darcy_pcg_tile_kernel(const double* __restrict__ cn, double* __restrict__ pn, in
                 const double piv = fc[k];
                 if (!(piv > 1e-300)) { ok_inv = false; break; }           // uniform: every thread reads the same pivot
                 const double ipiv = fast_rcp(piv);
-                const int kq = k / JP, kr = k - kq * JP;                  // column k is element kr of the threads with gp == kq
-                const int nq = (k + 1) / JP, nr = (k + 1) - nq * JP;
+                const int nq = (k + 1) / JP, nr = (k + 1) - nq * JP;      // column k+1 is element nr of the threads with gp == nq
                 if (worker) {
-                    const double f = fc[gi];
-                    double nextcol = 0.0;
+                    const double f = (gi == k) ? piv - 1.0 : fc[gi];
 #pragma unroll
-                    for (int jj = 0; jj < JP; ++jj) {
-                        const bool pivcol = gp == kq && jj == kr;
-                        const double rk = (pivcol ? 1.0 : pr[jj * PARTS + gp]) * ipiv;
-                        el[jj] = (gi == k) ? rk : ((pivcol ? 0.0 : el[jj]) - f * rk);
-                        if (jj == nr) nextcol = el[jj];
-                    }
+                    for (int jj = 0; jj < JP; ++jj) el[jj] = fma(-f, pr[jj * PARTS + gp] * ipiv, el[jj]);
                     if (k + 1 < 64) {
                         double* prn = prowB + ((k + 1) & 1) * 64;
+                        const double nextcol = pick(nr);
                         if (gi == k + 1) {
 #pragma unroll
                             for (int jj = 0; jj < JP; ++jj) prn[jj * PARTS + gp] = el[jj];
+                            if (gp == nq) prn[nr * PARTS + gp] = nextcol + 1.0;
                         }
                         if (gp == nq) fcolB[((k + 1) & 1) * 64 + gi] = nextcol;
                     }

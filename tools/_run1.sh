@@ -1,3 +1,2 @@
 timeout 900 python -m pytest tests/test_gpu_darcy.py -x -q -m gpu 2>&1 | tail -3
 timeout 300 python tools/bench_darcy.py 2>&1 | tail -4 | cut -c1-260
-CES_DARCY_COARSE=0 timeout 300 python tools/bench_darcy.py 2>&1 | tail -4 | cut -c1-260
