@@ -9,7 +9,7 @@
 //   Theta = U^T Phi^T                       DMMA GEMM (A_KM x B_KN)
 //   a     = exp(Theta)                      elementwise
 //   T1    = a S^T ; c_z = S T1_z            two DMMA GEMMs (stacked, then batched with the shared operand S)
-//   solve sum_faces w (p_i - p_nb) = h^2    darcy_pcg_tile_kernel: Jacobi-preconditioned CG, the member's vectors live in
+//   solve sum_faces w (p_i - p_nb) = h^2    darcy_pcg_tile_kernel: two-level preconditioned CG, the member's vectors live in
 //                                           registers + shared memory of a cluster of CTAs (row strips; halo rows and
 //                                           partial dot products travel through distributed shared memory)
 //   T2 = p S2^T ; P_z = S2 T2_z             spline back to the centres (two more GEMMs)
@@ -27,8 +27,9 @@ namespace cg = cooperative_groups;
 namespace ces {
 
 // ------------------------------------------------------------------------------------------------------------------
-// Conjugate-gradient solver.  Jacobi-preconditioned CG, restated so that one SM carries 4 032 nodes (everything but the
-// search direction in registers) and a cluster-wide reduction costs one DSMEM round trip instead of a cluster barrier:
+// Conjugate-gradient solver.  Preconditioned CG (Jacobi scaling + an aggregation coarse level, see CoarseGeom below), laid
+// out so that one SM carries 4 032 nodes (everything but the search direction in registers) and a cluster-wide reduction
+// costs one DSMEM round trip instead of a cluster barrier:
 //
 //  * symmetric Jacobi scaling: with s = diag(A)^(-1/2) the solver runs plain CG on A^ = S A S (unit diagonal), which is
 //    Jacobi-preconditioned CG on A in exact arithmetic (same iterates, r^.r^ = r.M^-1 r, so the stopping rule

@@ -121,3 +121,20 @@ def test_darcy_flow_example_script(tmp_path, monkeypatch):
         d = os.path.join(str(tmp_path), "ensembles", "darcy-flow-eks-000-%s-00" % str(eks.J).zfill(4))
         files = sorted(os.listdir(d))
         assert "metrics.pkl" in files and "ensemble_0000.npy" in files and "Gensemble_0000.npy" in files
+
+
+def test_solver_statistics_and_coarse_level(monkeypatch):
+    """ces_darcy_last_stats reports the batch it just solved; the aggregation coarse level changes the iteration count, not
+    the solution (same system, converged to the same relative residual)."""
+    rng = np.random.default_rng(11)
+    U = rng.standard_normal((64, 6))
+    m = cdarcy.model_trunc(Nmesh=64, p=64)
+    full = m.solve_ensemble(U, full_solution=True)
+    members, total, ms = m.last_stats()
+    assert members == 6 and ms > 0.0 and m.last_iterations <= total <= 6 * m.last_iterations
+    its_two_level = total
+    monkeypatch.setenv("CES_DARCY_COARSE", "0")
+    j = cdarcy.model_trunc(Nmesh=64, p=64)
+    jac = j.solve_ensemble(U, full_solution=True)
+    assert j.last_stats()[1] > 1.8 * its_two_level            # Jacobi alone needs ~2.5x the iterations at 64 x 64
+    assert _rel(full, jac) < 1e-10
