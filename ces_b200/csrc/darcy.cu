@@ -98,6 +98,11 @@ __device__ __forceinline__ double fast_rcp(double x) {
 // Gauss-Jordan, 64 x 64).  Per iteration the restriction P^T r rides on the r.r exchange (one extra double per aggregate),
 // every CTA applies the dense 64 x 64 inverse redundantly, and r.M^-1 r = r.r + rc.ec needs no further exchange -- the
 // number of DSMEM round trips per iteration stays two while the iteration count drops by ~2.7 (610 -> 225 at 128^2).
+// Between the two sits a third, purely local level: aggregates of 4 x 4 nodes (the tiles of two adjacent lanes) with a
+// diagonal solve, M^-1 = I + P1 diag(P1^T A^ P1)^-1 P1^T + P Ac^-1 P^T (additive multilevel).  It costs one shuffle and a
+// handful of flops per iteration -- its term of r.M^-1 r is added to the thread's partial before the exchange, and the
+// halo rows are pushed as r + P1 e1 so the neighbour's copy of the search direction stays exact -- and takes another
+// third off the iteration count (225 -> 150 at 128^2).
 // Members with a negative diagonal (see below) and shapes whose aggregates do not align run plain Jacobi scaling.
 struct CoarseGeom {
     int H, HQ, HG, NCR, NCC, NA;
@@ -275,6 +280,7 @@ darcy_pcg_tile_kernel(const double* __restrict__ cn, double* __restrict__ pn, in
     // PARTS threads of a coarse row then read consecutive words (no bank conflicts); dot products do not care about order
     auto cpos = [&](int j) -> int { return (j % JP) * PARTS + j / JP; };
     bool use_coarse = false;
+    double inv_d1 = 0.0;                                  // 1 / diagonal entry of this tile pair on the intermediate level
     if (COARSE) {
         bool any_signed = cta_signed;
         if (CLUSTER) {
@@ -289,16 +295,24 @@ darcy_pcg_tile_kernel(const double* __restrict__ cn, double* __restrict__ pn, in
             // of the same aggregate once (the other side adds its own), faces to another aggregate as off-diagonal entries
             const int NT = (int)blockDim.x;
             double cd = 0.0, cN = 0.0, cS = 0.0, cW = 0.0, cE = 0.0;
+            double own_int = 0.0, shared_faces = 0.0;
             if (active) {
                 double inner = ((wi[0] + wi[1]) + (wi[2] + wi[3])) + (((wv[1][0] + wv[1][1]) + (wv[2][0] + wv[2][1])) + (wv[3][0] + wv[3][1]));
                 cd = (double)nvalid + 2.0 * inner;
+                own_int = cd;
                 const double north = wv[0][0] + wv[0][1], south = wv[4][0] + wv[4][1];
                 const double west = (we_t[0] + we_t[KH + 1]) + (we_t[2 * (KH + 1)] + we_t[3 * (KH + 1)]);
                 const double east = (we_t[1] + we_t[KH + 2]) + (we_t[2 * (KH + 1) + 1] + we_t[3 * (KH + 1) + 1]);
+                shared_faces = (q & 1) ? west : east;           // the faces between the two tiles of a pair
                 if ((i0 - 1) % CG.H != 0) cd += north; else cN = north;
                 if ((i0 + 3) % CG.H != 0) cd += south; else cS = south;
                 if ((2 * q) % CG.H != 0) cd += west; else cW = west;
                 if ((2 * q + 2) % CG.H != 0) cd += east; else cE = east;
+            }
+            // intermediate level: aggregates of 4 x 4 nodes = the tiles of lanes (2m, 2m+1); only its diagonal is used
+            {
+                const double pair_d = (own_int + __shfl_xor_sync(0xffffffffu, own_int, 1)) + 2.0 * shared_faces;
+                inv_d1 = pair_d > 0.0 ? 1.0 / pair_d : 0.0;
             }
             double* st5 = Ainv;                         // staging: 5 x NT (the inverse is built afterwards)
             st5[tid] = cd; st5[NT + tid] = cN; st5[2 * NT + tid] = cS; st5[3 * NT + tid] = cW; st5[4 * NT + tid] = cE;
@@ -431,9 +445,12 @@ darcy_pcg_tile_kernel(const double* __restrict__ cn, double* __restrict__ pn, in
         for (int i = 0; i < 8; ++i) { const double2 v = w2[i]; t[i] = v.x + v.y; }
         return ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
     };
-    auto push_rows = [&]() {
-        if (first_group) st_async_f64x2(push_n_addr, r[0][0], r[0][1], push_n_bar);
-        if (last_group) st_async_f64x2(push_s_addr, r[3][0], r[3][1], push_s_bar);
+    // boundary rows of the strip for the neighbour's copy of p: r plus the correction of the intermediate level (e1 = 0
+    // without it), which the neighbour cannot know; it adds the coarse correction itself
+    auto push_rows = [&](double e1 = 0.0) {
+        const double e1a = q > 0 ? e1 : 0.0, e1b = q < KH - 1 ? e1 : 0.0;       // columns 0 and K-1 are boundary nodes
+        if (first_group) st_async_f64x2(push_n_addr, r[0][0] + e1a, r[0][1] + e1b, push_n_bar);
+        if (last_group) st_async_f64x2(push_s_addr, r[3][0] + e1a, r[3][1] + e1b, push_s_bar);
     };
     // part -> warp sum -> block sum -> every CTA of the cluster.  Every stage is a fixed xor-shuffle tree, identical in
     // every warp of every CTA, so all threads of the cluster see bit-identical sums and take identical decisions.
@@ -530,8 +547,17 @@ darcy_pcg_tile_kernel(const double* __restrict__ cn, double* __restrict__ pn, in
         return ((r[0][0] + r[0][1]) + (r[1][0] + r[1][1])) + ((r[2][0] + r[2][1]) + (r[3][0] + r[3][1]));
     };
 
-    push_rows();
-    reduce_send(part, 0, use_coarse, use_coarse ? tile_sum() : 0.0);
+    // intermediate level: r1 = sum of r over the tile pair, e1 = r1 / d1, and r1 e1 (half from each lane) joins r.r
+    double e1 = 0.0, ts0 = 0.0;
+    auto pair_level = [&](double& acc) {
+        ts0 = tile_sum();
+        const double r1 = ts0 + __shfl_xor_sync(0xffffffffu, ts0, 1);
+        e1 = r1 * inv_d1;
+        acc = fma(0.5 * r1, e1, acc);
+    };
+    if (COARSE && use_coarse) pair_level(part);
+    push_rows(e1);
+    reduce_send(part, 0, use_coarse, ts0);
     double rr = reduce_wait(0);
     if (COARSE && use_coarse) rr += coarse_apply();
     const double rr0 = rr;
@@ -554,8 +580,8 @@ darcy_pcg_tile_kernel(const double* __restrict__ cn, double* __restrict__ pn, in
 #pragma unroll
                 for (int a = 0; a < 4; ++a) {
                     // z = r + P ec; P has no entries on boundary / padding nodes (their r, p stay exactly 0)
-                    p[a][0] = fma(beta, p[a][0], CO ? r[a][0] + (((okmask >> (2 * a)) & 1u) ? ect : 0.0) : r[a][0]);
-                    p[a][1] = fma(beta, p[a][1], CO ? r[a][1] + (((okmask >> (2 * a + 1)) & 1u) ? ect : 0.0) : r[a][1]);
+                    p[a][0] = fma(beta, p[a][0], CO ? r[a][0] + (((okmask >> (2 * a)) & 1u) ? ect + e1 : 0.0) : r[a][0]);
+                    p[a][1] = fma(beta, p[a][1], CO ? r[a][1] + (((okmask >> (2 * a + 1)) & 1u) ? ect + e1 : 0.0) : r[a][1]);
                     pe_t[a * KH] = p[a][0];
                     po_t[a * KH] = p[a][1];
                 }
@@ -622,8 +648,9 @@ darcy_pcg_tile_kernel(const double* __restrict__ cn, double* __restrict__ pn, in
                     part1 = fma(SIGNED ? flip(r[a][1], 2 * a + 1) : r[a][1], r[a][1], part1);
                 }
             }
-            push_rows();
-            reduce_send((part0 + part1) + (part2 + part3), 0, CO && use_coarse, CO ? tile_sum() : 0.0);
+            if (CO && use_coarse) pair_level(part0);
+            push_rows(CO ? e1 : 0.0);
+            reduce_send((part0 + part1) + (part2 + part3), 0, CO && use_coarse, CO ? ts0 : 0.0);
             if (active) {           // next iteration's outer face weights: `ap` is dead, so this costs no registers
 #pragma unroll
                 for (int a = 0; a < 4; ++a) { nwl[a] = we_t[a * (KH + 1)]; nwr[a] = we_t[a * (KH + 1) + 1]; }
