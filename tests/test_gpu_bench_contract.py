@@ -46,3 +46,21 @@ def test_reference_arm_line():
         assert key in d, key
     assert d["impl"] == "reference" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["e2e"]["value"] == d["value"] == d["cpu_baseline"]["value"]
+
+
+def test_darcy_workload_line():
+    """--workload cfg2 (one ensemble Kalman iteration including the batched Darcy forward solve) prints the same contract
+    line; its roofline object describes the CG solver."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "cfg2", "--steps", "2", "--warmup", "3",
+                          "--no-cpu-baseline"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    for key in REQUIRED + ("clocks", "roofline"):
+        assert key in d, key
+    assert d["config"]["grid"] == 64 and d["config"]["J"] == 1024 and d["config"]["update"] == "eki"
+    assert d["value"] > 0 and d["gpu_launches"] > 0 and d["e2e"]["value"] > 0
+    r = d["roofline"]
+    assert "darcy_pcg_tile_kernel" in r["kernel"] and 0 < r["frac"] < 1 and 0.3 < r["share_of_step"] < 1
+    assert 20 < r["cg_iterations_mean"] < 400
