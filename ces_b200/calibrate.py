@@ -155,8 +155,22 @@ class enka(object):
         return np.concatenate([gs, ws[-1]])
 
     def G_pde_ens(self, theta, model, t):
-        """``G_pde`` for every column of theta (ces/calibrate.py:156-168).  The integrators of these models are the
-        user's (scipy) code and run on the host, one particle at a time or through joblib like the reference."""
+        """``G_pde`` for every column of theta (ces/calibrate.py:156-168): rows [:p] are the parameters, rows [p:] the
+        initial state of each particle; returns the statistics stacked on the final states.  The Lorenz models of
+        ``ces_b200.utils`` integrate the whole set in one device launch; any other model runs the user's (scipy) code on
+        the host, one particle at a time or through joblib like the reference."""
+        theta = np.asarray(theta, dtype=np.float64)
+        if getattr(model, 'device_kind', None) is not None and hasattr(model, 'evaluate_ensemble_pde'):
+            import torch
+
+            n = theta.shape[1]
+            U = torch.from_numpy(np.ascontiguousarray(theta[:self.p])).cuda()
+            W0 = torch.from_numpy(np.ascontiguousarray(theta[self.p:])).cuda()
+            G = torch.empty(self.n_obs, n, dtype=torch.float64, device="cuda")
+            Wend = torch.empty_like(W0)
+            if n:
+                model.evaluate_ensemble_pde(None, U, W0, t, G, Wend)
+            return np.vstack([G.cpu().numpy(), Wend.cpu().numpy()])
         if self.parallel:
             from joblib import Parallel, delayed
 
