@@ -91,10 +91,12 @@ __device__ __forceinline__ double l96_rhs(const double* __restrict__ w, int v, i
     if (v < ns) {
         const int k = v;
         const double xm1 = w[k == 0 ? ns - 1 : k - 1], xm2 = w[k < 2 ? ns + k - 2 : k - 2], xp1 = w[k == ns - 1 ? 0 : k + 1];
-        double ybar = 0.0;
         const double* y = w + ns + k * nf;
-        for (int l = 0; l < nf; ++l) ybar += y[l];
-        ybar /= (double)nf;
+        double ya = 0.0, yb = 0.0;                      // two chains: the slow threads are the critical path of a stage
+        int l = 0;
+        for (; l + 1 < nf; l += 2) { ya += y[l]; yb += y[l + 1]; }
+        if (l < nf) ya += y[l];
+        const double ybar = (ya + yb) / (double)nf;
         return -xm1 * (xm2 - xp1) - w[k] + pr.F - (pr.h * pr.c) * ybar;                      // :299-301
     }
     const int n = ns * nf, j = v - ns;
