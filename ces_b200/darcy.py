@@ -11,7 +11,7 @@ arithmetic runs in libces_b200.so (``ces_darcy_*``):
   1. Theta = U^T Phi^T            one DMMA GEMM; Phi holds the scaled 2-D DCT basis of the active KL modes
   2. a = exp(Theta)               cell-centre permeability
   3. c = S a S^T                  not-a-knot spline centres -> nodes as two DMMA GEMMs (stacked / batched)
-  4. -div(c grad p) = 1           Jacobi-preconditioned CG, member resident in shared memory (DSMEM cluster)
+  4. -div(c grad p) = 1           multilevel-preconditioned CG, member resident in registers + shared memory of a cluster
   5. P = S2 p S2^T                spline nodes -> centres (two more GEMMs), gather at ``obs_index``
 
 The constant operators Phi, S, S2 depend only on (Nmesh, alpha, tau, p) and are assembled once on the

@@ -168,7 +168,8 @@ int ces_profile_read(ces_handle_t h, double* gemm_d_ms, int64_t* launches, doubl
  * caller (ces_b200/darcy.py): PhiT (p x N^2, scaled 2-D inverse-DCT basis of the active modes), S (N x N, not-a-knot
  * spline cell centres -> nodes), S2 (N x N, nodes -> centres); obs_index (n_obs flat cell indices, row-major) or NULL.
  * ces_darcy_forward: U_dev (p x cols, ld = ldu) -> G_dev (n_obs x cols, or N^2 x cols when full_solution != 0), one
- * thread-block cluster per member running preconditioned CG (Jacobi scaling plus, for Nmesh in {32, 48, 64, 128}, an
+ * thread-block cluster per member running preconditioned CG (Jacobi scaling plus, for Nmesh in {32, 48, 64, 128}, a local
+ * 4 x 4-node level and an
  * aggregation coarse level of at most 64 unknowns) to relative residual `tol` in the preconditioner norm (<= 0: 1e-13)
  * with at most max_iter iterations (<= 0: 40 N); *iters_host receives the largest iteration count of the batch.
  * Environment (experiments only): CES_DARCY_COARSE=0 disables the coarse level, CES_DARCY_CLUSTER=2|4|8 asks for a larger
