@@ -312,7 +312,8 @@ darcy_pcg_tile_kernel(const double* __restrict__ cn, double* __restrict__ pn, in
             // intermediate level: aggregates of 4 x 4 nodes = the tiles of lanes (2m, 2m+1); only its diagonal is used
             {
                 const double pair_d = (own_int + __shfl_xor_sync(0xffffffffu, own_int, 1)) + 2.0 * shared_faces;
-                inv_d1 = pair_d > 0.0 ? 1.0 / pair_d : 0.0;
+                // (at Nmesh = 32 the coarse aggregates are these very 4 x 4 blocks: a second copy would over-correct)
+                inv_d1 = (CG.H > 4 && pair_d > 0.0) ? 1.0 / pair_d : 0.0;
             }
             double* st5 = Ainv;                         // staging: 5 x NT (the inverse is built afterwards)
             st5[tid] = cd; st5[NT + tid] = cN; st5[2 * NT + tid] = cS; st5[3 * NT + tid] = cW; st5[4 * NT + tid] = cE;

@@ -138,3 +138,21 @@ def test_solver_statistics_and_coarse_level(monkeypatch):
     jac = j.solve_ensemble(U, full_solution=True)
     assert j.last_stats()[1] > 1.8 * its_two_level            # Jacobi alone needs ~2.5x the iterations at 64 x 64
     assert _rel(full, jac) < 1e-10
+
+
+@pytest.mark.parametrize("N,p,scale", [(32, 24, 1.0), (48, 30, 1.0), (64, 64, 1.0), (64, 64, 10.0), (128, 256, 1.0)])
+def test_iteration_counts_match_the_pcg_oracle(N, p, scale):
+    """The kernel runs the algorithm oracle/darcy_pcg_oracle.py restates (scaled CG, 4 x 4 level, aggregation coarse
+    level, same stopping rule): besides the solution, its iteration counts must be the oracle's, member by member in sum
+    (different summation orders move a count by an iteration or two)."""
+    from oracle import darcy_pcg_oracle as dp
+
+    rng = np.random.default_rng(100 + N)
+    members = 3
+    U = scale * rng.standard_normal((p, members))
+    m = cdarcy.model_trunc(Nmesh=N, p=p)
+    ref = do.ModelTrunc(Nmesh=N, p=p)
+    m.solve_ensemble(U, full_solution=True)
+    _, total, _ = m.last_stats()
+    want = sum(dp.solve(ref.eval_rf(U[:, j]))[1] for j in range(members))
+    assert abs(total - want) <= max(3, 0.02 * want), (total, want)
