@@ -44,7 +44,7 @@ def test_as_written_metrics_equal_cheap(golden_steps):
 
 
 @pytest.mark.skipif(not rl.available(), reason="reference checkout not present (GPU box)")
-@pytest.mark.parametrize("ts", [None, "constant", "mix"])
+@pytest.mark.parametrize("ts", [None, "constant", "mix", "spectral"])
 def test_oracle_matches_live_reference(ts):
     d, k, J = 6, 9, 40
     pr = eo.linear_gaussian_problem(d, k, J, dense_gamma=True)
