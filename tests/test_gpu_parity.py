@@ -459,3 +459,24 @@ def test_target_size_properties():
         assert float((out[:, cols] - ref).abs().max() / ref.abs().max()) < TOL
     finally:
         eng.close()
+
+
+def test_golden_time_step_modes_of_the_real_reference():
+    """time_step = 'constant' / 'mix' / 'spectral' through the reference-facing methods against outputs of the REAL
+    reference (tests/golden/timestep_cases.npz), not just against the oracle."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "timestep_cases.npz"))
+    for name in g["names"]:
+        c = {key: g["%s/%s" % (name, key)] for key in ("y", "U0", "G", "Gamma", "mu", "Sigma0", "ustar", "xi")}
+        d, J = c["U0"].shape
+        for rule in ("eks", "aldi"):
+            for i, ms in enumerate(g["modes"]):
+                mode, th = str(ms).split("|")
+                th = [float(v) for v in th.split(",")] if th else []
+                s = _sampler(d, c["G"].shape[0], J, c["mu"], c["Sigma0"], c["ustar"], th)
+                s._ensure_metrics()
+                Uk = getattr(s, METHOD[rule])(c["y"], c["U0"], c["G"], c["Gamma"], 0, time_step=mode, delta_t=0.03, xi=c["xi"])
+                ref, (hk, t) = g["%s/%s/%d/Uk" % (name, rule, i)], g["%s/%s/%d/hk_t" % (name, rule, i)]
+                assert _rel(Uk, ref) < TOL, (name, rule, ms)
+                assert abs(s.metrics["t"][-1] - t) < TOL * t, (name, rule, ms)

@@ -148,3 +148,22 @@ def test_flop_models():
     assert abs(eo.algorithmic_flops(16384, 1024, 4096, gamma_dense=True) / 3.40e12 - 1) < 0.01
     assert abs(eo.algorithmic_flops(65536, 1024, 4096, gamma_dense=True) / 4.66e13 - 1) < 0.01
     assert abs(eo.algorithmic_flops(16384, 1024, 4096) / 2.852e12 - 1) < 0.01    # diagonal Gamma (bench workload)
+
+
+def test_oracle_matches_golden_time_step_modes():
+    """'constant', 'mix' and 'spectral' outputs of the real reference stored in tests/golden/timestep_cases.npz
+    (tests/golden/make_golden_timestep.py): this pin travels to machines without the reference checkout."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "timestep_cases.npz"))
+    for name in g["names"]:
+        c = {key: g["%s/%s" % (name, key)] for key in ("y", "U0", "G", "Gamma", "mu", "Sigma0", "ustar", "xi")}
+        for rule in ("eks", "aldi"):
+            for i, ms in enumerate(g["modes"]):
+                mode, th = str(ms).split("|")
+                th = [float(v) for v in th.split(",")] if th else None
+                o = eo.step(rule, c["y"], c["U0"], c["G"], c["Gamma"], c["mu"], c["Sigma0"], c["ustar"], c["xi"],
+                            time_step=mode, delta_t=0.03, t_last=th[-1] if th else None)
+                Uk, (hk, t) = g["%s/%s/%d/Uk" % (name, rule, i)], g["%s/%s/%d/hk_t" % (name, rule, i)]
+                assert np.abs(o["Uk"] - Uk).max() / np.abs(Uk).max() < TOL, (name, rule, ms)
+                assert abs(o["hk"] - hk) <= 1e-12 * hk and abs(o["t"] - t) <= 1e-12 * t, (name, rule, ms)
