@@ -38,9 +38,11 @@ library or without a GPU these classes raise.
 """
 from __future__ import print_function
 
+import hashlib
 import multiprocessing
 import os
 import pickle
+import zlib
 
 import numpy as np
 
@@ -51,13 +53,30 @@ _RULE_METHOD = {"eks": "eks_update", "aldi": "eks_update_aldi", "aldi_constant":
                 "eki": "eki_update"}
 
 
-def _fingerprint(a):
-    """Cheap identity of a problem array: object id, shape and a strided checksum.  Used to decide
-    whether the factorised problem data on the device is still current."""
+_SMALL_BYTES = 1 << 20
+_pool = None
+
+
+def _digest(a):
+    """Content digest of a problem array: every byte is read.  Small arrays: one blake2b; large ones (a dense Gamma at
+    k = 4096 is 128 MB): CRC-32 of 64 chunks on a thread pool (zlib releases the GIL) -- ~10 ms instead of 0.3 s."""
+    global _pool
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    raw = memoryview(a.view(np.uint8).reshape(-1))
+    if len(raw) <= _SMALL_BYTES:
+        return (a.shape, hashlib.blake2b(raw, digest_size=16).digest())
+    if _pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+
+        _pool = ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1))
+    step = -(-len(raw) // 64)
+    return (a.shape, tuple(_pool.map(lambda i: zlib.crc32(raw[i * step:(i + 1) * step]), range(64))))
+
+
+def _identity(a):
+    """Which buffer this is (not what it holds): lets an unchanged caller skip the synchronous digest of large arrays."""
     a = np.asarray(a)
-    flat = a.reshape(-1)
-    stride = max(1, flat.shape[0] // 4096)
-    return (id(a), a.shape, float(flat[::stride].sum()))
+    return (id(a), a.__array_interface__['data'][0], a.shape, a.strides, a.dtype.str)
 
 
 class enka(object):
@@ -251,13 +270,52 @@ class enka(object):
             self._problem_key = None
         return self._engine
 
-    def _sync_problem(self, eng, y_obs, Gamma):
+    def _sync_problem(self, eng, y_obs, Gamma, defer_large=False):
+        """Make the device copies of y_obs / Gamma / sigma / mu / ustar (and the cached factorisations) current.
+
+        The cache is keyed on the *content* of the five arrays (``_digest`` reads every byte), so an in-place edit is
+        never missed.  Small arrays are digested on the spot.  With ``defer_large`` (the per-call path of
+        ``eks_update*``), a large array whose buffer identity is unchanged is digested on a thread pool while the GPU
+        step runs; the returned callable reports afterwards whether its content had changed after all, in which case
+        the caller re-synchronises and repeats the step."""
         # AttributeError when mu / sigma / ustar are unset, like the reference (:433, :443)
         mu, sigma, ustar = self.mu, self.sigma, self.ustar
-        key = tuple(_fingerprint(a) for a in (y_obs, Gamma, sigma, mu, ustar))
-        if key != self._problem_key:
+        arrays = (y_obs, Gamma, sigma, mu, ustar)
+        idents = tuple(_identity(a) for a in arrays)
+        prev = self._problem_key
+        deferred = []
+        digests = []
+        for i, a in enumerate(arrays):
+            large = np.asarray(a).nbytes > _SMALL_BYTES
+            if defer_large and large and prev is not None and prev[0][i] == idents[i]:
+                digests.append(prev[1][i])
+                deferred.append(i)
+            else:
+                digests.append(_digest(a))
+        digests = tuple(digests)
+        if prev is None or prev[1] != digests:
             eng.set_problem(y_obs, Gamma, sigma, mu, ustar)
-            self._problem_key = key
+        self._problem_key = (idents, digests)
+        if not deferred:
+            return None
+        global _pool
+        if _pool is None:
+            _digest(arrays[deferred[0]])          # creates the pool
+        futures = [(i, _pool.submit(_digest, arrays[i])) for i in deferred]
+
+        def stale():
+            changed = False
+            new = list(self._problem_key[1])
+            for i, fut in futures:
+                dg = fut.result()
+                if dg != new[i]:
+                    new[i], changed = dg, True
+            if changed:
+                eng.set_problem(y_obs, Gamma, sigma, mu, ustar)
+                self._problem_key = (idents, tuple(new))
+            return changed
+
+        return stale
 
 
 class sampling(enka):
@@ -275,10 +333,18 @@ class sampling(enka):
             hk = 1. / (self._frobenius(D) + 1e-8)
         elif kind in ('constant', 'mix'):
             hk = const
+        elif kind == 'spectral':
+            # ces/calibrate.py:249-251 on a caller-owned (non-symmetric) D: radspec = eigvals(D).real.max().  The update
+            # methods never come here (they get lambda_max from the ensemble, csrc/eig.cu); this compatibility entry
+            # point has only the J x J matrix, so it runs the general eigenvalue routine on the device (cuSOLVER geev
+            # through torch.linalg.eigvals -- library code, off the hot path).
+            self._ensure_metrics()
+            radspec = self._eigvals_real_max(D)
+            self.radspec.append(radspec)
+            hk = 1. / radspec
         else:
-            raise NotImplementedError("time_step=%r with a caller-owned D: the update methods compute the spectral step "
-                                      "on the device from the ensemble (lambda_max(D) = lambda_max(Gamma^-1 C^pp)); "
-                                      "'adaptive' is undefined in the reference (ces/calibrate.py:255)" % (kind,))
+            raise NotImplementedError("time_step=%r: 'adaptive' calls a method the reference does not define "
+                                      "(ces/calibrate.py:255)" % (kind,))
         self._advance_time(hk)
         return hk
 
@@ -294,6 +360,15 @@ class sampling(enka):
                                              ctypes.c_void_p(Dd.data_ptr()), int(Dd.stride(0)), int(Dd.shape[0]),
                                              int(Dd.shape[1]), ctypes.byref(out)))
         return out.value
+
+    @staticmethod
+    def _eigvals_real_max(D):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("ces_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        Dd = torch.from_numpy(np.ascontiguousarray(D, dtype=np.float64)).cuda()
+        return float(torch.linalg.eigvals(Dd).real.max().item())
 
     def _advance_time(self, hk):
         # ces/calibrate.py:262-265 (first step <=> no time recorded yet)
@@ -333,13 +408,18 @@ class sampling(enka):
         fixed, resolve = self._step_options(rule, kwargs)
         U0 = np.asarray(U0, dtype=np.float64)
         eng = self._get_engine(U0.shape[1])
-        self._sync_problem(eng, y_obs, Gamma)
+        stale = self._sync_problem(eng, y_obs, Gamma, defer_large=True)
         xi = None
         if rule != 'eki':
             xi = self._draw_noise(U0.shape, kwargs)
-        Uk, hk, met = eng.step_host(rule, U0, np.asarray(Geval, dtype=np.float64)[:self.n_obs], xi, fixed_h=fixed,
-                                    switch=kwargs.get('switch', 1.), resolve=resolve,
-                                    formulation=kwargs.get('formulation', getattr(self, 'formulation', 'interaction')))
+        Gk = np.asarray(Geval, dtype=np.float64)[:self.n_obs]
+        opts = dict(fixed_h=fixed, switch=kwargs.get('switch', 1.), resolve=resolve,
+                    formulation=kwargs.get('formulation', getattr(self, 'formulation', 'interaction')))
+        Uk, hk, met = eng.step_host(rule, U0, Gk, xi, **opts)
+        if stale is not None and stale():
+            # a large problem array was edited in place since the previous call: the device copy has just been
+            # refreshed; repeat the step with the current data (the noise already drawn is reused)
+            Uk, hk, met = eng.step_host(rule, U0, Gk, xi, **opts)
         self._record(met, hk)
         if resolve == 'spectral':
             self.radspec.append(1. / hk)            # ces/calibrate.py:250

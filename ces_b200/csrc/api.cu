@@ -556,7 +556,7 @@ int ces_phase3d_spectral(ces_handle_t h, double* radspec_host, int* lanczos_step
     CES_TRY(valid(h, true));
     if (!h->Cpp) return fail(CES_ERR_STATE, "phase3d: ces_phase3b_cpp has not run%s", "");
     const int64_t k = h->k;
-    const int64_t mmax = k < 384 ? k : 384;
+    const int64_t mmax = k < 768 ? k : 768;
     if (!h->eig_ws) CES_TRY(dalloc(h, &h->eig_ws, (2 * (mmax + 1) + 2) * k + 4 * mmax + 8));
     return spectral_radius(h->st, h->Cpp, h->ldk, k, h->gamma_diag ? nullptr : h->Ginv, h->gamma_diag ? h->ginv_diag : nullptr,
                            h->eig_ws, mmax, radspec_host, lanczos_steps_host);

@@ -87,10 +87,11 @@ int set_identity(cudaStream_t st, double* A, int64_t ld, int64_t n) {
 int potrf_lower(cudaStream_t st, double* A, int64_t ld, int64_t n, double* Linv, int64_t ldinv, int* info_dev) {
     if (n < 1) return CES_OK;
     constexpr int kDiagSmem = (2 * NB * NBP + NB) * (int)sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[kMaxDevices] = {};
+    const int slot = device_slot();
+    if (!attr_set[slot]) {
         CES_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem));
-        attr_set = true;
+        attr_set[slot] = true;
     }
     for (int64_t j0 = 0; j0 < n; j0 += NB) {
         const int nb = (int)((n - j0) < NB ? (n - j0) : NB);

@@ -1,6 +1,7 @@
 // Shared helpers for the ces_b200 CUDA library (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include "../../include/ces_b200.h"   // status codes CES_OK / CES_ERR_*
@@ -8,7 +9,17 @@
 namespace ces {
 
 extern thread_local char g_last_error[512];
-extern long long g_launches;   // kernels launched by this library (ces_launch_count)
+extern std::atomic<long long> g_launches;   // kernels launched by this library (ces_launch_count); host threads may race
+
+// Ordinal of the calling thread's current device, clamped to the size of the per-device flag tables below.
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count are per DEVICE, not per process: every
+// "configured once" flag in this library is indexed by this slot.
+constexpr int kMaxDevices = 64;
+inline int device_slot() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    return dev < kMaxDevices ? dev : kMaxDevices - 1;
+}
 
 inline int fail(int code, const char* fmt, const char* a = "", long long b = 0) {
     snprintf(g_last_error, sizeof(g_last_error), fmt, a, b);
@@ -28,7 +39,7 @@ inline int fail(int code, const char* fmt, const char* a = "", long long b = 0) 
 // After a kernel launch: count it and surface launch-configuration errors.
 #define CES_LAUNCHED(n)                  \
     do {                                 \
-        ::ces::g_launches += (n);        \
+        ::ces::g_launches.fetch_add((n), std::memory_order_relaxed); \
         CES_CUDA(cudaGetLastError());    \
     } while (0)
 

@@ -726,12 +726,13 @@ static int pcg_tile_launch(DarcyModel* m, const double* cn, double* pn, int memb
     static const TileKernel table[32] = {CES_TILE_ROW(false, false), CES_TILE_ROW(true, false), CES_TILE_ROW(false, true),
                                          CES_TILE_ROW(true, true)};
 #undef CES_TILE_ROW
-    static size_t configured[32] = {};
+    static size_t configured[kMaxDevices][32] = {};
     const int slot = K / 16 - 1 + (m->tile_C > 1 ? 8 : 0) + (m->coarse ? 16 : 0);
     const TileKernel kernel = table[slot];
-    if (smem > configured[slot]) {
+    size_t& conf = configured[device_slot()][slot];
+    if (smem > conf) {
         CES_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[slot] = smem;
+        conf = smem;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(members * m->tile_C));

@@ -184,6 +184,7 @@ int spectral_radius(cudaStream_t st, const double* C, int64_t ld, int64_t n, con
     }
     double prev = -1.0, cur = 0.0;
     int agree = 0, steps = 0;
+    bool converged = (mmax == n);                                   // a full Krylov space is exact
     const int check_every = 4;
     for (int64_t j = 0; j < mmax; ++j) {
         const double* zj = Z + j * n;
@@ -207,13 +208,15 @@ int spectral_radius(cudaStream_t st, const double* C, int64_t ld, int64_t n, con
             CES_CUDA(cudaMemcpyAsync(host, state, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
             CES_CUDA(cudaStreamSynchronize(st));
             cur = host[3];
-            if (host[1] != 0.0) break;                              // invariant subspace: exact
-            if (fabs(cur - prev) <= 2e-15 * fabs(cur)) { if (++agree >= 2) break; } else agree = 0;
+            if (host[1] != 0.0) { converged = true; break; }        // invariant subspace: exact
+            if (fabs(cur - prev) <= 2e-15 * fabs(cur)) { if (++agree >= 2) { converged = true; break; } } else agree = 0;
             prev = cur;
         }
     }
     if (lambda_host) *lambda_host = cur;
-    if (steps_host) *steps_host = steps;
+    // a NEGATIVE step count reports that the iteration stopped at the cap without two agreeing estimates: the value
+    // is then a lower bound of lambda_max (Ritz values grow monotonically), i.e. hk = 1 / lambda may be too large
+    if (steps_host) *steps_host = converged ? steps : -steps;
     return CES_OK;
 }
 

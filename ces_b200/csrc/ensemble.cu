@@ -426,11 +426,13 @@ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint
 __global__ void __launch_bounds__(256) fill_normal_kernel(double* __restrict__ X, long long ld, int rows, long long cols,
                                                           long long col_offset, unsigned long long seed,
                                                           unsigned long long step) {
-    const long long pair = (long long)blockIdx.x * 256 + threadIdx.x;      // local column pair
+    // one thread per GLOBAL column pair (2g, 2g+1) that intersects this shard [col_offset, col_offset + cols): the
+    // stream depends only on (seed, step, row, global column), so any sharding -- odd offsets and odd widths
+    // included -- reproduces the columns of a single-GPU draw
+    const unsigned long long gpair = ((unsigned long long)col_offset >> 1) + (unsigned long long)blockIdx.x * 256 + threadIdx.x;
     const int row = blockIdx.y;
-    const long long j = 2 * pair;
+    const long long j = (long long)(2 * gpair) - col_offset;               // local index of the pair's first column (may be -1)
     if (j >= cols) return;
-    const unsigned long long gpair = (unsigned long long)(col_offset + j) >> 1;   // col_offset is even
     uint32_t c[4] = {(uint32_t)gpair, (uint32_t)(gpair >> 32), (uint32_t)row, (uint32_t)step};
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
@@ -445,14 +447,15 @@ __global__ void __launch_bounds__(256) fill_normal_kernel(double* __restrict__ X
     const double rad = sqrt(-2.0 * log(u1));
     double sn, cs;
     sincospi(2.0 * u2, &sn, &cs);
-    X[(size_t)row * ld + j] = rad * cs;
+    if (j >= 0) X[(size_t)row * ld + j] = rad * cs;
     if (j + 1 < cols) X[(size_t)row * ld + j + 1] = rad * sn;
 }
 int fill_normal(cudaStream_t st, double* X, int64_t ld, int64_t rows, int64_t cols, int64_t col_offset, uint64_t seed,
                 uint64_t step) {
     if (rows < 1 || cols < 1) return CES_OK;
-    if (col_offset & 1) return fail(CES_ERR_INVALID, "fill_normal: column offset must be even%s", "");
-    dim3 grid((unsigned)ceil_div(ceil_div(cols, 2), 256), (unsigned)rows);
+    if (col_offset < 0) return fail(CES_ERR_INVALID, "fill_normal: negative column offset%s", "");
+    const int64_t pairs = ((col_offset + cols - 1) >> 1) - (col_offset >> 1) + 1;
+    dim3 grid((unsigned)ceil_div(pairs, 256), (unsigned)rows);
     fill_normal_kernel<<<grid, 256, 0, st>>>(X, ld, (int)rows, cols, col_offset, seed, step);
     CES_LAUNCHED(1);
     return CES_OK;

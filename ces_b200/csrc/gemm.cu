@@ -6,14 +6,15 @@
 namespace ces {
 
 thread_local char g_last_error[512] = "";
-long long g_launches = 0;
+std::atomic<long long> g_launches{0};
 
 template <int AM, int BM_, int ROWS>
 static int launch_one(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& a, dim3 grid) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[kMaxDevices] = {};
+    const int slot = device_slot();
+    if (!attr_set[slot]) {
         CES_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<AM, BM_, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-        attr_set = true;
+        attr_set[slot] = true;
     }
     gemm_dmma_kernel<AM, BM_, ROWS><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ma, mb, a);
     CES_LAUNCHED(1);
@@ -60,7 +61,8 @@ int gemm(cudaStream_t st, const GemmCall& c) {
     a.kblocks_per_split = 0;
     a.splitk_ws = nullptr;
     {
-        static int sms = 0;
+        static int sms_of[kMaxDevices] = {};
+        int& sms = sms_of[device_slot()];
         if (!sms) {
             int dev = 0;
             if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1)

@@ -303,7 +303,8 @@ int small_step(cudaStream_t st, const SmallStepCall& c) {
     a.S = c.S;
     const int threads = (int)round_up(c.J, 32);
     const size_t smem = ((size_t)(c.k + c.p) * c.J + (SK + SP) + 3 * SP * SP + SP + 8) * sizeof(double);
-    static size_t configured = 0;
+    static size_t configured_of[kMaxDevices] = {};
+    size_t& configured = configured_of[device_slot()];
     if (smem > 48 * 1024 && smem > configured) {
         CES_CUDA(cudaFuncSetAttribute(small_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;

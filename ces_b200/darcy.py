@@ -110,7 +110,7 @@ class model(object):
         self.type = 'map'
         self.flag_noise = False
         self.tol = 1e-13            # relative residual of the CG solve (the reference solves directly)
-        self.max_iter = 0           # 0: 20 N
+        self.max_iter = 0           # 0: the library default, 40 N iterations
         self._dev = None
 
     # engine management of the reference: nothing to start here
@@ -170,22 +170,28 @@ class model(object):
         S2 = np.ascontiguousarray(spline_operator(nodes, centres))
         lib = _lib.load()
         h = ctypes.c_void_p()
-        stream = torch.cuda.current_stream().cuda_stream
+        self._stream = torch.cuda.current_stream()          # the handle launches on this stream from now on
         _lib.check(lib.ces_darcy_create(N, int(self.p), _lib.host_ptr(phiT), _lib.host_ptr(S), _lib.host_ptr(S2),
                                         obs.ctypes.data if obs.size else None, int(obs.size),
-                                        ctypes.c_void_p(stream), ctypes.byref(h)))
+                                        ctypes.c_void_p(self._stream.cuda_stream), ctypes.byref(h)))
         self._dev = (h, key)
         return h
 
+    def _forward(self, h, U_dev, G_dev, full):
+        import torch
+        from .engine import stream_guard
+
+        iters = ctypes.c_int()
+        with stream_guard(torch, self._stream):
+            _lib.check(_lib.load().ces_darcy_forward(h, ctypes.c_void_p(U_dev.data_ptr()), int(U_dev.stride(0)),
+                                                     int(U_dev.shape[1]), ctypes.c_void_p(G_dev.data_ptr()),
+                                                     int(G_dev.stride(0)), 1 if full else 0, float(self.tol),
+                                                     int(self.max_iter), ctypes.byref(iters)))
+        self.last_iterations = iters.value
+
     def evaluate_ensemble(self, engine, U_dev, G_dev):
         """G[:, j] = observations of member j (``enka.G_ens``); U_dev (p, cols), G_dev (n_obs, cols) on the GPU."""
-        h = self._handle(True)
-        iters = ctypes.c_int()
-        _lib.check(_lib.load().ces_darcy_forward(h, ctypes.c_void_p(U_dev.data_ptr()), int(U_dev.stride(0)),
-                                                 int(U_dev.shape[1]), ctypes.c_void_p(G_dev.data_ptr()),
-                                                 int(G_dev.stride(0)), 0, float(self.tol), int(self.max_iter),
-                                                 ctypes.byref(iters)))
-        self.last_iterations = iters.value
+        self._forward(self._handle(True), U_dev, G_dev, False)
         return G_dev
 
     def last_stats(self):
@@ -207,12 +213,7 @@ class model(object):
         h = self._handle(not full_solution)
         Ud = torch.from_numpy(U).cuda()
         Gd = torch.empty(rows, n, dtype=torch.float64, device="cuda")
-        iters = ctypes.c_int()
-        _lib.check(_lib.load().ces_darcy_forward(h, ctypes.c_void_p(Ud.data_ptr()), int(Ud.stride(0)), n,
-                                                 ctypes.c_void_p(Gd.data_ptr()), int(Gd.stride(0)),
-                                                 1 if full_solution else 0, float(self.tol), int(self.max_iter),
-                                                 ctypes.byref(iters)))
-        self.last_iterations = iters.value
+        self._forward(h, Ud, Gd, full_solution)
         return Gd.cpu().numpy()
 
     def __call__(self, xi, full_solution=False):

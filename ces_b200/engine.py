@@ -5,6 +5,7 @@ current CUDA stream and ``torch.distributed`` for the collectives between phases
 when the ensemble is sharded by particle columns over several GPUs
 (SURVEY.md section 8e).  All arithmetic happens in libces_b200.so.
 """
+import contextlib
 import ctypes
 
 import numpy as np
@@ -55,9 +56,7 @@ def run_phases(phases, buffer, comm, p, k, rule, resolve=None, formulation="inte
             dist.all_reduce(t, group=group) if op is None else dist.all_reduce(t, op=op, group=group)
 
         def allreduce_slice(t, lo, hi, op=None):
-            part = t[0, lo:hi].clone()
-            allreduce(part, op)
-            t[0, lo:hi] = part
+            allreduce(t[0, lo:hi], op)        # a contiguous view: reduced in place, no staging copies
     else:
         rank = 0
 
@@ -127,6 +126,22 @@ def run_phases(phases, buffer, comm, p, k, rule, resolve=None, formulation="inte
     phases["update"](keep)
 
 
+@contextlib.contextmanager
+def stream_guard(torch, lib_stream):
+    """A library handle launches on the stream that was current when it was created.  Torch work issued around it
+    (collectives, copies, noise) must be ordered with those launches: when the caller has since switched streams
+    (``with torch.cuda.stream(s): eks.run(...)``), the library stream first waits for the caller's stream, becomes the
+    current stream for the duration of the call, and the caller's stream waits for it afterwards."""
+    cur = torch.cuda.current_stream()
+    if cur.cuda_stream == lib_stream.cuda_stream:
+        yield
+        return
+    lib_stream.wait_stream(cur)
+    with torch.cuda.stream(lib_stream):
+        yield
+    cur.wait_stream(lib_stream)
+
+
 class _DeviceView(object):
     """Zero-copy torch view of a library-owned device buffer (``__cuda_array_interface__``)."""
 
@@ -176,6 +191,9 @@ class Engine(object):
         self._hk = ctypes.c_double()
         self._met = (ctypes.c_double * 4)()
 
+    def on_stream(self):
+        return stream_guard(self.torch, self.stream)
+
     def close(self):
         if getattr(self, "h", None):
             self.lib.ces_destroy(self.h)
@@ -222,11 +240,10 @@ class Engine(object):
         """(rows, cols) standard normal noise for this rank's columns, generated on the device (ces_fill_normal);
         identical to the corresponding columns of a single-GPU draw with the same (seed, step)."""
         torch = self.torch
-        if self.col_lo % 2:
-            raise ValueError("device noise needs an even shard offset (use an even shard width)")
         if out is None:
             out = torch.empty(rows, self.cols, dtype=torch.float64, device="cuda")
         if self.cols:
+          with self.on_stream():
             _lib.check(self.lib.ces_fill_normal(ctypes.c_void_p(self.stream.cuda_stream), int(seed), int(step),
                                                 ctypes.c_void_p(out.data_ptr()), int(out.stride(0)), int(rows),
                                                 int(self.cols), int(self.col_lo)))
@@ -243,6 +260,10 @@ class Engine(object):
 
     # ------------------------------------------------------------------ one update
     def step(self, rule, U, G, xi, out=None, fixed_h=None, switch=1.0, resolve=None, formulation="interaction"):
+        with self.on_stream():
+            return self._step(rule, U, G, xi, out, fixed_h, switch, resolve, formulation)
+
+    def _step(self, rule, U, G, xi, out, fixed_h, switch, resolve, formulation):
         """One update on this rank's columns.  U (p, cols), G (k, cols), xi (p, cols) are float64 CUDA
         tensors; returns (U_next, hk, metrics dict).  ``fixed_h`` gives the step size ('constant', 'mix' after
         spin-up); ``resolve`` asks for the hk C^pp + Gamma re-solve of D (see ``run_phases``)."""
@@ -274,7 +295,12 @@ class Engine(object):
             def spectral():
                 lam, steps = ctypes.c_double(), ctypes.c_int()
                 _lib.check(lib.ces_phase3d_spectral(h, ctypes.byref(lam), ctypes.byref(steps)))
-                self.last_radspec, self.last_lanczos_steps = lam.value, steps.value
+                self.last_radspec, self.last_lanczos_steps = lam.value, abs(steps.value)
+                if steps.value < 0:
+                    import warnings
+
+                    warnings.warn("time_step='spectral': Lanczos stopped after %d steps without converging; lambda_max "
+                                  "(%.6e) is a lower bound, hk may be too large" % (-steps.value, lam.value), RuntimeWarning)
                 return lam.value
 
             def update(keep):
@@ -346,6 +372,10 @@ class Engine(object):
     # ------------------------------------------------------------------ forward maps
     def forward_map(self, kind, U, G, A=None, lda=0, b=None, params=None):
         """G[:, j] = model(U[:, j]) on the device for the ces.utils maps (enka.G_ens)."""
+        with self.on_stream():
+            return self._forward_map(kind, U, G, A, lda, b, params)
+
+    def _forward_map(self, kind, U, G, A, lda, b, params):
         Up, ldu = self._dev(U)
         Gp, ldg = self._dev(G)
         Ap = ctypes.c_void_p(A.data_ptr()) if A is not None else None

@@ -117,7 +117,9 @@ int ces_phase3c_resolve(ces_handle_t h, int rule);
  * ces_phase3b_cpp and the all-reduce of "cpp", ces_phase3d_spectral returns lambda_max(Gamma^-1 C^pp), which equals the
  * largest eigenvalue of D (the non-zero spectrum of D = E^T (Gamma^-1 R / J) is that of Gamma^-1 R E^T / J = Gamma^-1 C^pp,
  * real and non-negative), by Lanczos in the Gamma^-1 inner product with full re-orthogonalisation; *lanczos_steps
- * receives the number of steps taken.  Phase 4 is then called with CES_TS_FIXED and 1 / radspec. */
+ * receives the number of steps taken -- NEGATED when the iteration reached its cap (min(k, 768) steps) without two
+ * agreeing estimates: the value is then only a lower bound of lambda_max.  Phase 4 is then called with CES_TS_FIXED
+ * and 1 / radspec. */
 int ces_phase3d_spectral(ces_handle_t h, double* radspec_host, int* lanczos_steps_host);
 /* Factored formulation (opt-in; the same update to rounding without forming the J x J matrix):
  *   V = (1/J) (U~ E^T) W   and   ||D||_F^2 = sum((E E^T) o (W W^T)) / J^2.

@@ -113,5 +113,10 @@ def test_device_normal_noise_is_standard_normal_and_shard_invariant():
         part = torch.empty(8, 1000, dtype=torch.float64, device="cuda")
         _lib.check(eng.lib.ces_fill_normal(st, 7, 3, ctypes.c_void_p(part.data_ptr()), part.stride(0), 8, 1000, 5000))
         assert torch.equal(part, a[:, 5000:6000])
+        # odd offsets and odd widths (J = 1000 on 8 ranks gives shards of 125 columns) draw the same columns too
+        for off, w in ((125, 125), (4999, 1), (4999, 2), (7, 1000)):
+            part = torch.full((8, w), float("nan"), dtype=torch.float64, device="cuda")
+            _lib.check(eng.lib.ces_fill_normal(st, 7, 3, ctypes.c_void_p(part.data_ptr()), part.stride(0), 8, w, off))
+            assert torch.equal(part, a[:, off:off + w]), (off, w)
     finally:
         eng.close()

@@ -424,8 +424,14 @@ def test_timestep_method_with_an_explicit_interaction_matrix():
     assert h2 == 1. / 15 and abs(s.metrics["t"][-1] - (h1 + h2)) < 1e-15
     h3 = s.timestep_method(D, None, None, None, None, time_step="mix", spinup=0.01, delta_t=0.25)
     assert h3 == 0.25
+    # 'spectral' on a caller-owned, non-symmetric D (ces/calibrate.py:249-251): radspec = eigvals(D).real.max()
+    t_before = s.metrics["t"][-1]
+    h4 = s.timestep_method(D, None, None, None, None, time_step="spectral")
+    lam = np.linalg.eigvals(D).real.max()
+    assert abs(h4 - 1.0 / lam) < 1e-10 * abs(h4) and abs(s.radspec[-1] - lam) < 1e-10 * abs(lam)
+    assert abs(s.metrics["t"][-1] - (t_before + h4)) < 1e-15
     with pytest.raises(NotImplementedError):
-        s.timestep_method(D, None, None, None, None, time_step="spectral")
+        s.timestep_method(D, None, None, None, None, time_step="adaptive")
 
 
 def test_target_size_properties():
