@@ -407,12 +407,25 @@ class sampling(enka):
         self._ensure_metrics()
         fixed, resolve = self._step_options(rule, kwargs)
         U0 = np.asarray(U0, dtype=np.float64)
-        eng = self._get_engine(U0.shape[1])
+        group = getattr(self, 'group', None)
+        local = bool(kwargs.get('local_shard', False)) and group is not None
+        eng = self._get_engine(self.J if local else U0.shape[1], group)
         stale = self._sync_problem(eng, y_obs, Gamma, defer_large=True)
+        Gk = np.asarray(Geval, dtype=np.float64)[:self.n_obs]
         xi = None
         if rule != 'eki':
-            xi = self._draw_noise(U0.shape, kwargs)
-        Gk = np.asarray(Geval, dtype=np.float64)[:self.n_obs]
+            # the full (p, J) draw on every rank -- the same global stream as the reference -- unless the caller
+            # passes its own (possibly sharded) noise
+            xi = self._draw_noise((U0.shape[0], eng.J), kwargs)
+        if eng.nranks > 1 and not local:
+            # every rank was called with the full arrays (the reference's calling convention): take this rank's columns;
+            # the full U_next is gathered below
+            lo, hi = eng.col_lo, eng.col_hi
+            U0, Gk = U0[:, lo:hi], Gk[:, lo:hi]
+            if xi is not None and xi.shape[1] == eng.J:
+                xi = xi[:, lo:hi]
+        elif local and xi is not None and xi.shape[1] == eng.J and eng.J != eng.cols:
+            xi = xi[:, eng.col_lo:eng.col_hi]
         opts = dict(fixed_h=fixed, switch=kwargs.get('switch', 1.), resolve=resolve,
                     formulation=kwargs.get('formulation', getattr(self, 'formulation', 'interaction')))
         Uk, hk, met = eng.step_host(rule, U0, Gk, xi, **opts)
@@ -420,6 +433,8 @@ class sampling(enka):
             # a large problem array was edited in place since the previous call: the device copy has just been
             # refreshed; repeat the step with the current data (the noise already drawn is reused)
             Uk, hk, met = eng.step_host(rule, U0, Gk, xi, **opts)
+        if eng.nranks > 1 and not local:
+            Uk = eng.gather_columns_host(Uk)
         self._record(met, hk)
         if resolve == 'spectral':
             self.radspec.append(1. / hk)            # ces/calibrate.py:250

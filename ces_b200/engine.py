@@ -304,6 +304,10 @@ class Engine(object):
                 return lam.value
 
             def update(keep):
+                ev = getattr(self, "_xi_ready", None)
+                if ev is not None:                  # sharded host step: the noise was uploaded on a side stream
+                    torch.cuda.current_stream().wait_event(ev)
+                    self._xi_ready = None
                 if keep == "spectral":
                     kind, val = _lib.TS_FIXED, 1.0 / self.last_radspec
                 else:
@@ -332,12 +336,14 @@ class Engine(object):
         return out, float(self._hk.value), met
 
     def step_host(self, rule, U, G, xi, fixed_h=None, switch=1.0, resolve=None, formulation="interaction"):
-        """The same update on host numpy arrays (single GPU): the copies to and from the device are part
-        of the call.  This is what ``sampling.eks_update*`` invoke."""
-        if self.nranks != 1:
-            raise RuntimeError("step_host is single-GPU; shard device tensors and call step()")
+        """The same update on host numpy arrays: the copies to and from the device are part of the call.  This is what
+        ``sampling.eks_update*`` invoke.  Single GPU: (p, J) / (k, J) arrays through ``ces_step_host``.  Column-sharded
+        (``nranks > 1``): this rank's (p, cols) / (k, cols) shards in, its (p, cols) shard of U_next out, the phases
+        with their collectives in between (``_step_host_sharded``)."""
         if formulation not in _lib.FORMULATIONS:
             raise ValueError("formulation must be 'interaction' or 'factored'")
+        if self.nranks != 1:
+            return self._step_host_sharded(rule, U, G, xi, fixed_h, switch, resolve, formulation)
         if resolve is not None:
             # non-default time_step: the phase-by-phase device path, with explicit copies around it
             torch = self.torch
@@ -368,6 +374,58 @@ class Engine(object):
                                           _lib.host_ptr(out), ctypes.byref(self._hk), self._met))
         met = {key: float(self._met[i]) for i, key in enumerate(_METRIC_KEYS)}
         return out, float(self._hk.value), met
+
+    def _pinned(self, name, shape):
+        """Reusable page-locked staging array (numpy view of a torch pinned tensor)."""
+        key = ("pin", name, tuple(shape))
+        if key not in self._views:
+            self._views[key] = self.torch.empty(tuple(shape), dtype=self.torch.float64, pin_memory=True)
+        return self._views[key]
+
+    def _step_host_sharded(self, rule, U, G, xi, fixed_h, switch, resolve, formulation):
+        """Column shard on host arrays: H2D of (U, G, xi) shards on a copy stream -- xi is needed only by the last
+        phase, so its upload overlaps the interaction GEMMs --, the phases with their collectives, D2H of the shard of
+        U_next into page-locked memory."""
+        torch = self.torch
+        with self.on_stream():
+            U = np.ascontiguousarray(U, dtype=np.float64)
+            G = np.ascontiguousarray(G, dtype=np.float64)
+            assert U.shape == (self.p, self.cols) and G.shape == (self.k, self.cols), (U.shape, G.shape, self.cols)
+            if "h2d" not in self._views:
+                self._views["h2d"] = torch.cuda.Stream()
+                for name, rows in (("U", self.p), ("G", self.k), ("xi", self.p), ("out", self.p)):
+                    self._views["dev_" + name] = torch.empty(rows, max(self.cols, 1), dtype=torch.float64, device="cuda")
+            copy_st = self._views["h2d"]
+            Ud, Gd, Xd, Od = (self._views["dev_" + n] for n in ("U", "G", "xi", "out"))
+            main = torch.cuda.current_stream()
+            copy_st.wait_stream(main)               # the previous step's readers of the staging buffers
+            Ud.copy_(torch.from_numpy(U), non_blocking=True)
+            Gd.copy_(torch.from_numpy(G), non_blocking=True)
+            xi_ready = None
+            if xi is not None:
+                xi = np.ascontiguousarray(xi, dtype=np.float64)
+                assert xi.shape == U.shape
+                with torch.cuda.stream(copy_st):
+                    Xd.copy_(torch.from_numpy(xi), non_blocking=True)
+                    xi_ready = torch.cuda.Event()
+                    xi_ready.record(copy_st)
+            self._xi_ready = xi_ready
+            out, hk, met = self._step(rule, Ud, Gd, Xd if xi is not None else None, Od, fixed_h, switch, resolve, formulation)
+            host = torch.empty((self.p, self.cols), dtype=torch.float64, pin_memory=self.p * self.cols * 8 >= (1 << 20))
+            host.copy_(out, non_blocking=True)
+            main.synchronize()
+            return host.numpy(), hk, met
+
+    def gather_columns_host(self, local):
+        """Full (rows, J) host array from every rank's (rows, cols) host shard (all ranks receive it)."""
+        torch = self.torch
+        local = np.ascontiguousarray(local, dtype=np.float64)
+        rows = local.shape[0]
+        pad = torch.zeros(rows, self.Jl, dtype=torch.float64, device="cuda")
+        pad[:, :self.cols] = torch.from_numpy(local).cuda()
+        full = torch.empty(self.nranks, rows, self.Jl, dtype=torch.float64, device="cuda")
+        self.dist.all_gather_into_tensor(full.view(-1), pad.view(-1), group=self.group)
+        return full.permute(1, 0, 2).reshape(rows, self.nranks * self.Jl)[:, :self.J].cpu().numpy()
 
     # ------------------------------------------------------------------ forward maps
     def forward_map(self, kind, U, G, A=None, lda=0, b=None, params=None):

@@ -8,16 +8,27 @@ raises ``TabError`` on Python 3.  The file is read, tab-expanded to 4 columns in
 memory and exec'd into a private module; nothing under /root/reference is
 modified.  ``ces.utils`` imports cleanly and is loaded through importlib.
 
-The reference only exists in the build container.  On the GPU box
-``available()`` is False and every caller must skip / fall back to the
-committed golden vectors.
+The reference itself only exists in the build container (/root/reference).  ``oracle/stage_reference.py`` copies the
+three files of the update path, unmodified, to the git-ignored ``baseline/_ref/`` so that they travel to the GPU box
+for ``bench.py --impl reference``; this loader looks at /root/reference (or ``CES_REFERENCE_ROOT``) first and there
+second.  Tests must not depend on either: on the GPU box they use the committed golden vectors.
 """
 import importlib.util
 import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("CES_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+
+
+def _find_root():
+    for root in (os.environ.get("CES_REFERENCE_ROOT"), "/root/reference", _STAGED):
+        if root and os.path.isfile(os.path.join(root, "ces", "calibrate.py")):
+            return root
+    return os.environ.get("CES_REFERENCE_ROOT", "/root/reference")
+
+
+REFERENCE_ROOT = _find_root()
 
 _cache = {}
 

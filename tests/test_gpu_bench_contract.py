@@ -36,8 +36,12 @@ def test_gpu_arm_line():
     r = d["roofline"]
     assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and r["peak"] > 10 and 0 < r["frac"] < 1.2
     c = d["cpu_baseline"]
-    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
+    # "reference" when the unmodified reference files travelled in baseline/_ref/ (oracle/stage_reference.py), else the port
+    assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["value"] > 0 and c["sample"] and c["J_sample"] == 1024
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    # the correctness probe of the timed step: hk through the Gram identity, 128 particles of U_next from the definition
+    p = d["parity"]
+    assert p["ok"] is True and p["hk_rel"] <= 1e-10 and p["probe_rel"] <= 1e-10 and p["tol"] == 1e-10
 
 
 def test_reference_arm_line():
@@ -46,6 +50,22 @@ def test_reference_arm_line():
         assert key in d, key
     assert d["impl"] == "reference" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["e2e"]["value"] == d["value"] == d["cpu_baseline"]["value"]
+    assert d["config"]["J_sample"] == d["cpu_baseline"]["J_sample"] == 1024 and d["cpu_baseline"]["cores"] >= 1
+
+
+def test_cfg1_run_line():
+    """--workload cfg1: BASELINE.json configs[0] through sampling.run(T=1000) (ces/calibrate.py:270-416)."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "cfg1", "--no-cpu-baseline"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    for key in REQUIRED + ("roofline",):
+        assert key in d, key
+    assert d["steps"] == 1000 and d["config"]["J"] == 100 and d["value"] > 0 and d["e2e"]["value"] > 0 and d["gpu_launches"] >= 1000
+    # the run converges to the analytic posterior mean of the notebook problem (linear.ipynb:695-697)
+    assert abs(d["posterior_mean"][0] + 1.0367) < 0.1 and abs(d["posterior_mean"][1] - 2.0870) < 0.1
 
 
 def test_darcy_workload_line():
