@@ -26,7 +26,9 @@ EXPORTS = (
     "ces_profile_enable", "ces_profile_read", "ces_darcy_create", "ces_darcy_destroy", "ces_darcy_forward", "ces_darcy_last_stats",
     "ces_peek_step_size", "ces_phase3b_cpp", "ces_phase3c_resolve", "ces_phase3f_products", "ces_phase3f_finish",
     "ces_fill_normal", "ces_phase3_blocks", "ces_frobenius", "ces_phase3d_spectral", "ces_lorenz63_forward",
-    "ces_lorenz96_forward",
+    "ces_lorenz96_forward", "ces_set_pending_output", "ces_timeline_enable",
+    "ces_timeline_mark", "ces_timeline_read", "ces_host_begin", "ces_host_sums_g", "ces_host_centre_g", "ces_host_sums_u",
+    "ces_host_centre_u", "ces_host_interact_own", "ces_host_update",
 )
 
 _i64, _int, _dbl, _vp = ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_void_p
@@ -75,6 +77,17 @@ def load():
                              ctypes.POINTER(_dbl), ctypes.POINTER(_dbl)]
     lib.ces_step_host.argtypes = [_vp, _int, _int, _dbl, _dbl, _int, _dp, _dp, _dp, _dp,
                                   ctypes.POINTER(_dbl), ctypes.POINTER(_dbl)]
+    lib.ces_set_pending_output.argtypes = [_vp, _dp]
+    lib.ces_host_begin.argtypes = [_vp, _int, _int, _dp, _dp, _dp, ctypes.POINTER(_int), ctypes.POINTER(_i64)]
+    lib.ces_host_sums_g.argtypes = [_vp, _int]
+    lib.ces_host_centre_g.argtypes = [_vp, _int]
+    lib.ces_host_sums_u.argtypes = [_vp]
+    lib.ces_host_centre_u.argtypes = [_vp]
+    lib.ces_host_interact_own.argtypes = [_vp]
+    lib.ces_host_update.argtypes = [_vp, _int, _dbl, _dp, ctypes.POINTER(_dbl), ctypes.POINTER(_dbl)]
+    lib.ces_timeline_enable.argtypes = [_vp, _int]
+    lib.ces_timeline_mark.argtypes = [_vp, ctypes.c_char_p]
+    lib.ces_timeline_read.argtypes = [_vp, ctypes.c_char_p, _i64, ctypes.POINTER(_dbl), _i64, ctypes.POINTER(_i64)]
     lib.ces_forward_map.argtypes = [_vp, _int, _dp, _i64, _dp, _dp, _dp, _i64, _dp, _i64]
     lib.ces_buffer.argtypes = [_vp, ctypes.c_char_p, ctypes.POINTER(_vp), ctypes.POINTER(_i64),
                                ctypes.POINTER(_i64), ctypes.POINTER(_i64)]

@@ -43,12 +43,22 @@ struct ces_handle_s {
     double *stage_U = nullptr, *stage_G = nullptr, *stage_xi = nullptr, *stage_out = nullptr;
     double* pending_out = nullptr;      // host destination of stage_out, copied inside phase 4 before its final sync
     int64_t pending_rows = 0;
+    int hb_nchunk = 1, hb_formulation = 0;   // state of a host step in progress (ces_host_begin ... ces_host_update)
+    bool hb_have_xi = false;
+    int64_t hb_bound[5] = {0, 0, 0, 0, 0};
     cudaStream_t aux_st = nullptr;      // chol(C^uu) runs here, hidden behind the D / V GEMMs of the main stream
     cudaEvent_t cuu_ready = nullptr, chol_done = nullptr;
     bool chol_pending = false;
-    cudaStream_t copy_st = nullptr;     // uploads xi while phases 1-3 run
-    cudaEvent_t copy_ev = nullptr, start_ev = nullptr;
+    cudaStream_t copy_st = nullptr;     // ces_step_host: uploads G (row chunks), U and xi while the main stream computes
+    cudaEvent_t copy_ev = nullptr, start_ev = nullptr, u_ev = nullptr;
+    cudaEvent_t g_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t out_st = nullptr;      // phase 4: downloads finished column chunks of U_next while the next chunk computes
+    cudaEvent_t out_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::vector<void*> allocs;
+    // optional per-phase timeline (ces_timeline_*): named CUDA events recorded on the stream a phase runs on
+    bool timeline = false;
+    std::vector<std::pair<std::string, cudaEvent_t>> marks;
+    std::vector<cudaEvent_t> mark_pool;
     // optional event timing of the D = E^T W launches
     bool profile = false;
     std::vector<cudaEvent_t> ev_pool;
@@ -73,6 +83,16 @@ int dalloc(ces_handle_t h, double** out, int64_t n) {
     h->allocs.push_back(ptr);
     *out = static_cast<double*>(ptr);
     return CES_OK;
+}
+
+// Timeline mark: a timing event on `s` (default: the main stream) when the timeline is enabled; free otherwise.
+void mark(ces_handle_t h, const char* name, cudaStream_t s = nullptr) {
+    if (!h->timeline) return;
+    cudaEvent_t e;
+    if (!h->mark_pool.empty()) { e = h->mark_pool.back(); h->mark_pool.pop_back(); }
+    else if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, s ? s : h->st);
+    h->marks.emplace_back(name, e);
 }
 
 double* e_block(ces_handle_t h, int r) { return h->E_all + (size_t)r * h->k * h->ldJ; }
@@ -217,12 +237,18 @@ int ces_destroy(ces_handle_t h) {
     if (h->copy_st) cudaStreamSynchronize(h->copy_st);
     for (void* ptr : h->allocs) cudaFree(ptr);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    for (auto& m : h->marks) cudaEventDestroy(m.second);
+    for (cudaEvent_t e : h->mark_pool) cudaEventDestroy(e);
     if (h->cuu_ready) cudaEventDestroy(h->cuu_ready);
     if (h->chol_done) cudaEventDestroy(h->chol_done);
     if (h->aux_st) cudaStreamDestroy(h->aux_st);
     if (h->copy_ev) cudaEventDestroy(h->copy_ev);
     if (h->start_ev) cudaEventDestroy(h->start_ev);
+    if (h->u_ev) cudaEventDestroy(h->u_ev);
+    for (cudaEvent_t e : h->g_ev) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->out_ev) if (e) cudaEventDestroy(e);
     if (h->copy_st) cudaStreamDestroy(h->copy_st);
+    if (h->out_st) { cudaStreamSynchronize(h->out_st); cudaStreamDestroy(h->out_st); }
     if (h->hS) cudaFreeHost(h->hS);
     delete h;
     cudaGetLastError();
@@ -287,28 +313,33 @@ int ces_set_problem(ces_handle_t h, const double* y, const double* Gamma, const 
 int ces_phase1_sums(ces_handle_t h, const double* U, int64_t ldu, const double* G, int64_t ldg) {
     CES_TRY(valid(h, true));
     if (!U || !G || ldu < h->cols || ldg < h->cols) return fail(CES_ERR_INVALID, "phase1: bad ensemble pointers%s", "");
+    mark(h, "phase1:begin");
     if (h->cols == 0) {
         CES_CUDA(cudaMemsetAsync(h->sums, 0, (h->k + h->p) * sizeof(double), h->st));
         return CES_OK;
     }
     CES_TRY(row_sums(h->st, G, ldg, h->k, h->cols, h->sums));
     CES_TRY(row_sums(h->st, U, ldu, h->p, h->cols, h->sums + h->k));
+    mark(h, "phase1:end");
     return CES_OK;
 }
 
-int ces_phase2_centre(ces_handle_t h, int rule, const double* U, int64_t ldu, const double* G, int64_t ldg) {
-    CES_TRY(valid(h, true));
-    if (rule < CES_RULE_EKS || rule > CES_RULE_EKI) return fail(CES_ERR_INVALID, "unknown update rule %s%lld", "", rule);
-    if (!U || !G) return fail(CES_ERR_INVALID, "phase2: null ensemble%s", "");
-    const int64_t p = h->p, k = h->k, ld = h->ldJ, cols = h->cols;
+// ---- phase 2 in pieces (ces_step_host pipelines them against the row-chunked upload of G) -----------------------
+// Rows [r0, r0 + nr) of the forward outputs: E, W (diagonal Gamma) or R (dense), c = mean - y.  Row means are per row
+// over the particles, so a row chunk is self-contained.
+static int centre_g_rows(ces_handle_t h, const double* G, int64_t ldg, int64_t r0, int64_t nr) {
+    const int64_t ld = h->ldJ;
     const double invJ = 1.0 / (double)h->Jg;
+    double* E = e_block(h, h->rank) + r0 * ld;
+    double* WR = (h->gamma_diag ? h->W : h->R) + r0 * ld;
+    return centre_g(h->st, G + r0 * ldg, ldg, nr, h->cols, h->sums + r0, invJ, h->y + r0,
+                    h->gamma_diag ? h->ginv_diag + r0 : nullptr, E, WR, ld, h->cvec + r0);
+}
+
+// After every row of G is centred: W = Gamma^-1 R for dense Gamma, z = Gamma^-1 c, data-space diagnostics.
+static int finish_g(ces_handle_t h) {
+    const int64_t k = h->k, ld = h->ldJ;
     cudaStream_t st = h->st;
-    h->last_rule = rule;
-    double* E = e_block(h, h->rank);
-    double* Ut = ut_block(h, h->rank);
-    // --- forward outputs: E, R / W, c, z, data-space diagnostics
-    CES_TRY(centre_g(st, G, ldg, k, cols, h->sums, invJ, h->y, h->gamma_diag ? h->ginv_diag : nullptr, E,
-                     h->gamma_diag ? h->W : h->R, ld, h->cvec));
     if (h->gamma_diag) {
         CES_TRY(scale_vector(st, h->ginv_diag, h->cvec, h->zvec, k));
     } else {
@@ -319,10 +350,18 @@ int ces_phase2_centre(ces_handle_t h, int rule, const double* U, int64_t ldu, co
         CES_TRY(gemm(st, g));
         CES_TRY(matvec(st, h->Ginv, h->ldk, k, h->cvec, h->zvec));
     }
-    const int nyk = form_row_blocks(k, ld), nyp = form_row_blocks(p, ld);
-    CES_TRY(data_forms(st, E, h->W, ld, k, h->cvec, h->zvec, h->qpart));
-    CES_TRY(finish_forms(st, h->qpart, nyk, ld, cols, true, h->formpart, h->S + S_SELF_DATA));
-    // --- parameters: U~, Z, parameter-space diagnostics
+    const int nyk = form_row_blocks(k, ld);
+    CES_TRY(data_forms(st, e_block(h, h->rank), h->W, ld, k, h->cvec, h->zvec, h->qpart));
+    return finish_forms(st, h->qpart, nyk, ld, h->cols, true, h->formpart, h->S + S_SELF_DATA);
+}
+
+// Parameters: U~, Z, parameter-space diagnostics, local part of C^uu.
+static int centre_u_all(ces_handle_t h, int rule, const double* U, int64_t ldu) {
+    const int64_t p = h->p, k = h->k, ld = h->ldJ, cols = h->cols;
+    const double invJ = 1.0 / (double)h->Jg;
+    cudaStream_t st = h->st;
+    double* Ut = ut_block(h, h->rank);
+    const int nyp = form_row_blocks(p, ld);
     CES_TRY(centre_u(st, U, ldu, p, cols, h->sums + k, invJ, h->mu, h->ustar, h->sigma_diag ? h->sinv_diag : nullptr, Ut,
                      h->sigma_diag ? h->Z : h->Y, ld, h->qpart));
     CES_TRY(finish_forms(st, h->qpart, nyp, ld, cols, false, h->formpart, h->S + S_SELF_BIAS));
@@ -334,17 +373,27 @@ int ces_phase2_centre(ces_handle_t h, int rule, const double* U, int64_t ldu, co
         CES_TRY(gemm(st, g));
     }
     // --- local part of C^uu = U~ U~^T / (J-1) (+1e-8 I once)   (K6; :424 uses 1/J, :476/:512 use 1/(J-1))
-    {
-        GemmCall g;
-        g.a_mode = A_MK; g.b_mode = B_NK;
-        g.M = (int)p; g.N = (int)p; g.K = (int)h->Jl;
-        g.A = Ut; g.lda = ld; g.B = Ut; g.ldb = ld; g.C = h->Cuu; g.ldc = h->ldp;
-        g.alpha = (rule == CES_RULE_EKS) ? 1.0 / (double)h->Jg : 1.0 / (double)(h->Jg - 1);
-        g.flags = GEMM_C_LOWER_ONLY;
-        g.splits = h->syrk_splits; g.splitk_ws = h->splitk_ws;
-        g.diag_add = (h->rank == 0) ? 1e-8 : 0.0;
-        CES_TRY(gemm(st, g));
-    }
+    GemmCall g;
+    g.a_mode = A_MK; g.b_mode = B_NK;
+    g.M = (int)p; g.N = (int)p; g.K = (int)h->Jl;
+    g.A = Ut; g.lda = ld; g.B = Ut; g.ldb = ld; g.C = h->Cuu; g.ldc = h->ldp;
+    g.alpha = (rule == CES_RULE_EKS) ? 1.0 / (double)h->Jg : 1.0 / (double)(h->Jg - 1);
+    g.flags = GEMM_C_LOWER_ONLY;
+    g.splits = h->syrk_splits; g.splitk_ws = h->splitk_ws;
+    g.diag_add = (h->rank == 0) ? 1e-8 : 0.0;
+    return gemm(st, g);
+}
+
+int ces_phase2_centre(ces_handle_t h, int rule, const double* U, int64_t ldu, const double* G, int64_t ldg) {
+    CES_TRY(valid(h, true));
+    if (rule < CES_RULE_EKS || rule > CES_RULE_EKI) return fail(CES_ERR_INVALID, "unknown update rule %s%lld", "", rule);
+    if (!U || !G) return fail(CES_ERR_INVALID, "phase2: null ensemble%s", "");
+    h->last_rule = rule;
+    mark(h, "phase2:begin");
+    CES_TRY(centre_g_rows(h, G, ldg, 0, h->k));
+    CES_TRY(finish_g(h));
+    CES_TRY(centre_u_all(h, rule, U, ldu));
+    mark(h, "phase2:end");
     return CES_OK;
 }
 
@@ -355,14 +404,31 @@ int ces_phase2_centre(ces_handle_t h, int rule, const double* U, int64_t ldu, co
 // batched D launch (blockIdx.y = block, one D slot each) and ONE batched V launch whose per-block partial products are
 // summed by the split-K reduce kernel -- with P = 8 ranks and small shards a per-block launch has too few tiles to
 // fill 148 SMs (256 tiles = 1.73 waves at Jl = 2048).
-static int interaction_loops(ces_handle_t h, const double* Wsrc, bool accumulate_ssq, int first, int count) {
+//
+// A call may cover only part of the work (ces_step_host pipelines the interaction against the upload of G):
+// column panels [c_begin, c_end) of this rank's particles, contraction rows [k_lo, k_hi) of the D GEMM -- chunks after
+// the first accumulate into the panel (beta = 1; the sum of squares is taken from the stored values of the last
+// chunk) --, and the D and V products separately.
+struct InteractRange {
+    int64_t c_begin = 0, c_end = -1;     // -1: Jl
+    int64_t k_lo = 0, k_hi = -1;         // -1: k
+    bool do_d = true, do_v = true;
+    bool reset = true;                   // first call of a step: restart the sum-of-squares partials
+    bool finish = true;                  // last call of a step: reduce the partials into S[S_SSQ]
+};
+
+static int interaction_loops(ces_handle_t h, const double* Wsrc, bool accumulate_ssq, int first, int count,
+                             const InteractRange& rg = InteractRange()) {
     const int64_t p = h->p, k = h->k, ld = h->ldJ;
     cudaStream_t st = h->st;
-    if (first == 0) h->ssq_used = 0;
+    if (first == 0 && rg.reset) h->ssq_used = 0;
     int64_t npart = h->ssq_used;
     const double invJ = 1.0 / (double)h->Jg;
-    for (int64_t c0 = 0; c0 < h->Jl; c0 += h->panel) {
-        const int64_t nc = (h->Jl - c0) < h->panel ? (h->Jl - c0) : h->panel;
+    const int64_t c_end = rg.c_end < 0 ? h->Jl : rg.c_end;
+    const int64_t k_lo = rg.k_lo, k_hi = rg.k_hi < 0 ? k : rg.k_hi;
+    const bool last_chunk = (k_hi == k);
+    for (int64_t c0 = rg.c_begin; c0 < c_end; c0 += h->panel) {
+        const int64_t nc = (c_end - c0) < h->panel ? (c_end - c0) : h->panel;
         int i = first;
         while (i < first + count) {
             const int s0 = (h->rank + i) % h->nranks;
@@ -373,19 +439,20 @@ static int interaction_loops(ces_handle_t h, const double* Wsrc, bool accumulate
                 while (i + run < first + count && s0 + run < h->nranks) ++run;
             GemmCall g1;
             g1.a_mode = A_KM; g1.b_mode = B_KN;
-            g1.M = (int)h->Jl; g1.N = (int)nc; g1.K = (int)k;
-            g1.A = e_block(h, s0); g1.lda = ld;
-            g1.B = Wsrc + c0; g1.ldb = ld;
+            g1.M = (int)h->Jl; g1.N = (int)nc; g1.K = (int)(k_hi - k_lo);
+            g1.A = e_block(h, s0) + k_lo * ld; g1.lda = ld;
+            g1.B = Wsrc + k_lo * ld + c0; g1.ldb = ld;
             g1.C = h->D; g1.ldc = h->ldD;
             g1.alpha = invJ;
+            g1.beta = k_lo > 0 ? 1.0 : 0.0;
             g1.batch = run; g1.a_batch_rows = k; g1.c_batch_elems = h->Jl * h->ldD;
-            if (accumulate_ssq) {
+            if (rg.do_d && accumulate_ssq && last_chunk) {
                 const int64_t tiles = (int64_t)gemm_tiles(g1.M, g1.N) * run;
                 if (npart + tiles > h->ssq_cap) return fail(CES_ERR_STATE, "phase3: partial-sum buffer too small%s", "");
                 g1.ssq_partials = h->ssq_partials + npart;
                 npart += tiles;
             }
-            if (h->profile) {
+            if (rg.do_d && h->profile) {
                 while (h->ev_pool.size() < h->ev_used + 2) {
                     cudaEvent_t e;
                     CES_CUDA(cudaEventCreate(&e));
@@ -393,12 +460,13 @@ static int interaction_loops(ces_handle_t h, const double* Wsrc, bool accumulate
                 }
                 CES_CUDA(cudaEventRecord(h->ev_pool[h->ev_used], st));
             }
-            CES_TRY(gemm(st, g1));
-            if (h->profile) {
+            if (rg.do_d) CES_TRY(gemm(st, g1));
+            if (rg.do_d && h->profile) {
                 CES_CUDA(cudaEventRecord(h->ev_pool[h->ev_used + 1], st));
                 h->ev_used += 2;
-                h->prof_flops += 2.0 * (double)k * (double)g1.M * (double)g1.N * run;
+                h->prof_flops += 2.0 * (double)g1.K * (double)g1.M * (double)g1.N * run;
             }
+            if (!rg.do_v) { i += run; continue; }
             GemmCall g2;
             g2.a_mode = A_MK; g2.b_mode = B_KN;
             g2.M = (int)p; g2.N = (int)nc; g2.K = (int)h->Jl;
@@ -434,7 +502,7 @@ static int interaction_loops(ces_handle_t h, const double* Wsrc, bool accumulate
         }
     }
     h->ssq_used = npart;
-    if (accumulate_ssq && first + count == h->nranks) CES_TRY(sum_vector(st, h->ssq_partials, npart, h->S + S_SSQ));
+    if (accumulate_ssq && rg.finish && first + count == h->nranks) CES_TRY(sum_vector(st, h->ssq_partials, npart, h->S + S_SSQ));
     return CES_OK;
 }
 
@@ -445,7 +513,10 @@ int ces_phase3_interact(ces_handle_t h, int rule, int skip_interaction) {
     if (rule != h->last_rule) return fail(CES_ERR_STATE, "phase3: rule differs from phase2%s", "");
     CES_TRY(start_cholesky(h, rule));
     if (skip_interaction) return CES_OK;       // 'constant' step size: D is formed once, by ces_phase3c_resolve
-    return interaction_loops(h, h->W, true, 0, h->nranks);
+    mark(h, "phase3:begin");
+    CES_TRY(interaction_loops(h, h->W, true, 0, h->nranks));
+    mark(h, "phase3:end");
+    return CES_OK;
 }
 
 int ces_phase3_blocks(ces_handle_t h, int rule, int first, int count) {
@@ -454,7 +525,10 @@ int ces_phase3_blocks(ces_handle_t h, int rule, int first, int count) {
     if (first < 0 || count < 0 || first + count > h->nranks) return fail(CES_ERR_INVALID, "phase3_blocks: bad block range%s", "");
     if (first == 0) CES_TRY(start_cholesky(h, rule));
     if (count == 0) return CES_OK;
-    return interaction_loops(h, h->W, true, first, count);
+    mark(h, first == 0 ? "phase3:own:begin" : "phase3:rest:begin");
+    CES_TRY(interaction_loops(h, h->W, true, first, count));
+    mark(h, first == 0 ? "phase3:own:end" : "phase3:rest:end");
+    return CES_OK;
 }
 
 static int start_cholesky(ces_handle_t h, int rule) {
@@ -688,10 +762,12 @@ int ces_phase4_update(ces_handle_t h, int rule, int ts_kind, double fixed_h, con
         xi_use = h->xi_pad; ldxi_use = ld;
     }
 
+    mark(h, "phase4:begin");
     if (h->chol_pending) {              // the factor of C^uu from the side stream
         CES_CUDA(cudaStreamWaitEvent(st, h->chol_done, 0));
         h->chol_pending = false;
     }
+    mark(h, "phase4:chol_ready");
     const int kind = (rule == CES_RULE_ALDI_CONSTANT) ? 2 : (ts_kind == CES_TS_FIXED ? 1 : 0);
     if (ts_kind != CES_TS_KEEP || rule == CES_RULE_ALDI_CONSTANT) CES_TRY(step_scalars(st, S, kind, fixed_h, alphaJ));
 
@@ -701,24 +777,69 @@ int ces_phase4_update(ces_handle_t h, int rule, int ts_kind, double fixed_h, con
     noise.A = h->L; noise.lda = h->ldp; noise.B = xi_use; noise.ldb = ldxi_use; noise.C = Uout; noise.ldc = ldo;
     noise.alpha_dev = S + S_SQRT2H; noise.beta = 1.0; noise.flags = GEMM_A_LOWER_TRI;
 
-    if (h->cols > 0) {
+    // With a host destination (ces_step_host / ces_set_pending_output) the explicit rules finish U_next in column
+    // chunks: chunk c is copied to the host on a second stream while chunk c + 1 is computed, so that only the last
+    // chunk's download is exposed.  Chunk starts are multiples of 128 columns (TMA operand alignment).
+    // Chunk widths are whole double-waves of the p x p GEMMs (2 x SMs tiles), so chunking adds no partial wave.  The
+    // download (p x cols x 8 B over PCIe) takes longer than assembling U_next, so it should start as early as possible:
+    // a first chunk of one unit, then the rest in three pieces; exposed = the first chunk's assembly + whatever of the
+    // download the assembly could not cover.
+    int64_t cstart[6] = {0, h->cols, h->cols, h->cols, h->cols, h->cols};
+    int nchunks = 1;
+    if (h->pending_out && rule != CES_RULE_EKS && h->cols >= 4096) {
+        const int64_t tiles_m = ceil_div(p, p <= 64 ? 64 : GEMM_BM);
+        int64_t unit_blocks = (2 * (int64_t)gemm_sm_count()) / tiles_m;
+        if (unit_blocks < 1) unit_blocks = 1;
+        int64_t unit = unit_blocks * GEMM_BN;
+        const int64_t eighth = round_up(ceil_div(h->cols, 8), GEMM_BN);
+        if (unit > eighth) unit = eighth;                       // few row tiles: a wave is wider than the ensemble
+        const int64_t units = h->cols / unit;                   // whole units; the last chunk takes the remainder
+        if (units >= 2) {
+            cstart[nchunks++] = unit;
+            const int64_t pieces = units - 1 >= 3 ? 3 : units - 1;
+            for (int64_t i = 1; i < pieces; ++i) cstart[nchunks++] = unit + (units - 1) * i / pieces * unit;
+        }
+    }
+    bool downloaded = false;
+    if (nchunks > 1) {
+        if (!h->out_st) {
+            CES_CUDA(cudaStreamCreateWithFlags(&h->out_st, cudaStreamNonBlocking));
+            for (cudaEvent_t& e : h->out_ev) CES_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        downloaded = true;
+    }
+    cstart[nchunks] = h->cols;
+    for (int chunk = 0; chunk < nchunks && h->cols > 0 && rule != CES_RULE_EKS; ++chunk) {
+        const int64_t c0 = cstart[chunk], nc = cstart[chunk + 1] - c0;
+        GemmCall nz = noise;
+        nz.N = (int)nc; nz.B = xi_use ? xi_use + c0 : nullptr; nz.C = Uout + c0;
         if (rule == CES_RULE_ALDI) {
             // U + h alpha_J U~ - h V - h C Z + sqrt(2h) L xi      (:484-488)
-            CES_TRY(axpbypcz(st, p, h->cols, 1.0, U, ldu, 1.0, S + S_H_ALPHA, Ut, ld, 1.0, S + S_NEG_H, h->V, ld, Uout, ldo));
+            CES_TRY(axpbypcz(st, p, nc, 1.0, U + c0, ldu, 1.0, S + S_H_ALPHA, Ut + c0, ld, 1.0, S + S_NEG_H, h->V + c0, ld,
+                             Uout + c0, ldo));
             GemmCall g;
             g.a_mode = A_MK; g.b_mode = B_KN;
-            g.M = (int)p; g.N = (int)h->cols; g.K = (int)p;
-            g.A = h->Cuu; g.lda = h->ldp; g.B = h->Z; g.ldb = ld; g.C = Uout; g.ldc = ldo;
+            g.M = (int)p; g.N = (int)nc; g.K = (int)p;
+            g.A = h->Cuu; g.lda = h->ldp; g.B = h->Z + c0; g.ldb = ld; g.C = Uout + c0; g.ldc = ldo;
             g.alpha_dev = S + S_NEG_H; g.beta = 1.0;
             CES_TRY(gemm(st, g));
-            CES_TRY(gemm(st, noise));
+            CES_TRY(gemm(st, nz));
         } else if (rule == CES_RULE_ALDI_CONSTANT) {
             // U + h drift + sqrt(2h) L xi                         (:525-527)
-            CES_TRY(axpbypcz(st, p, h->cols, 1.0, U, ldu, 1.0, S + S_H, h->T, ld, 0.0, nullptr, nullptr, 0, Uout, ldo));
-            CES_TRY(gemm(st, noise));
-        } else if (rule == CES_RULE_EKI) {
-            CES_TRY(axpbypcz(st, p, h->cols, 1.0, U, ldu, 1.0, S + S_NEG_H, h->V, ld, 0.0, nullptr, nullptr, 0, Uout, ldo));
-        } else {
+            CES_TRY(axpbypcz(st, p, nc, 1.0, U + c0, ldu, 1.0, S + S_H, h->T + c0, ld, 0.0, nullptr, nullptr, 0, Uout + c0, ldo));
+            CES_TRY(gemm(st, nz));
+        } else {                                                   // EKI
+            CES_TRY(axpbypcz(st, p, nc, 1.0, U + c0, ldu, 1.0, S + S_NEG_H, h->V + c0, ld, 0.0, nullptr, nullptr, 0, Uout + c0, ldo));
+        }
+        if (downloaded) {
+            CES_CUDA(cudaEventRecord(h->out_ev[chunk], st));
+            CES_CUDA(cudaStreamWaitEvent(h->out_st, h->out_ev[chunk], 0));
+            CES_CUDA(cudaMemcpy2DAsync(h->pending_out + c0, h->cols * sizeof(double), Uout + c0, ldo * sizeof(double),
+                                       nc * sizeof(double), h->pending_rows, cudaMemcpyDeviceToHost, h->out_st));
+        }
+    }
+    if (h->cols > 0 && rule == CES_RULE_EKS) {
+        {
             // semi-implicit EKS (:443-447) with (I + h C S^-1)^-1 = S (S + h C)^-1   
             if (!h->M) { CES_TRY(dalloc(h, &h->M, p * h->ldp)); }
             if (!h->Minv) { CES_TRY(dalloc(h, &h->Minv, round_up(p, CHOL_NB) * kLinvLd)); }
@@ -745,11 +866,14 @@ int ces_phase4_update(ces_handle_t h, int rule, int ts_kind, double fixed_h, con
         }
     }
     CES_CUDA(cudaMemcpyAsync(h->hS, S, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (h->pending_out) {               // ces_step_host: result copy rides on the same final synchronisation
-        const size_t wbytes = h->Jl * sizeof(double);
-        if (ldo == h->Jl) CES_CUDA(cudaMemcpyAsync(h->pending_out, Uout, (size_t)h->pending_rows * wbytes, cudaMemcpyDeviceToHost, st));
+    if (h->pending_out && !downloaded && h->cols > 0) {   // result copy rides on the same final synchronisation
+        const size_t wbytes = h->cols * sizeof(double);
+        if (ldo == h->cols) CES_CUDA(cudaMemcpyAsync(h->pending_out, Uout, (size_t)h->pending_rows * wbytes, cudaMemcpyDeviceToHost, st));
         else CES_CUDA(cudaMemcpy2DAsync(h->pending_out, wbytes, Uout, ldo * sizeof(double), wbytes, h->pending_rows, cudaMemcpyDeviceToHost, st));
     }
+    h->pending_out = nullptr;           // one-shot
+    mark(h, "phase4:computed");
+    if (downloaded) { mark(h, "phase4:downloaded", h->out_st); CES_CUDA(cudaStreamSynchronize(h->out_st)); }
     CES_TRY(check_info(h, "cov(U)"));   // synchronises the stream
     if (hk_host) *hk_host = h->hS[S_H];
     if (metrics_host) {
@@ -815,12 +939,10 @@ int ces_step(ces_handle_t h, int rule, int ts_kind, double fixed_h, double switc
     return ces_phase4_update(h, rule, ts_kind, fixed_h, U, ldu, xi, ldxi, Uout, ldo, hk_host, metrics_host);
 }
 
-int ces_step_host(ces_handle_t h, int rule, int ts_kind, double fixed_h, double switch_, int formulation, const double* U,
-                  const double* G, const double* xi, double* Uout, double* hk_host, double* metrics_host) {
-    CES_TRY(valid(h, true));
-    if (h->nranks != 1) return fail(CES_ERR_STATE, "ces_step_host is single-GPU%s", "");
-    if (!U || !G || !Uout) return fail(CES_ERR_INVALID, "ces_step_host: null pointer%s", "");
-    const int64_t p = h->p, k = h->k, J = h->Jl, ld = h->ldJ;
+// ---- the update on HOST buffers, as pieces (include/ces_b200.h: "host steps") -----------------------------------
+// ces_step_host (single GPU) strings them together; a column-sharded caller runs its collectives in between.
+static int host_staging(ces_handle_t h) {
+    const int64_t p = h->p, k = h->k, ld = h->ldJ;
     if (!h->stage_U) {
         CES_TRY(dalloc(h, &h->stage_U, p * ld));
         CES_TRY(dalloc(h, &h->stage_G, k * ld));
@@ -831,27 +953,167 @@ int ces_step_host(ces_handle_t h, int rule, int ts_kind, double fixed_h, double 
         CES_CUDA(cudaStreamCreateWithFlags(&h->copy_st, cudaStreamNonBlocking));
         CES_CUDA(cudaEventCreateWithFlags(&h->copy_ev, cudaEventDisableTiming));
         CES_CUDA(cudaEventCreateWithFlags(&h->start_ev, cudaEventDisableTiming));
+        CES_CUDA(cudaEventCreateWithFlags(&h->u_ev, cudaEventDisableTiming));
+        for (cudaEvent_t& e : h->g_ev) CES_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
-    const size_t wb = J * sizeof(double), pb = ld * sizeof(double);
-    auto h2d = [&](double* dst, const double* src, int64_t rows, cudaStream_t s) -> cudaError_t {
-        if (ld == J) return cudaMemcpyAsync(dst, src, (size_t)rows * wb, cudaMemcpyHostToDevice, s);
-        return cudaMemcpy2DAsync(dst, pb, src, wb, wb, rows, cudaMemcpyHostToDevice, s);
-    };
-    const bool small = h->use_small && formulation == CES_FORM_INTERACTION && small_step_eligible(h->p, h->k, h->Jl);
-    // the noise is needed only by phase 4: upload it on a second stream while phases 1-3 compute
-    // (ordered after the previous step's use of the staging buffer through start_ev); tiny problems keep
-    // everything on one stream -- the extra events would cost more than the copy
-    if (xi && small) {
-        CES_CUDA(h2d(h->stage_xi, xi, p, h->st));
-    } else if (xi) {
-        CES_CUDA(cudaEventRecord(h->start_ev, h->st));
-        CES_CUDA(cudaStreamWaitEvent(h->copy_st, h->start_ev, 0));
-        CES_CUDA(h2d(h->stage_xi, xi, p, h->copy_st));
+    return CES_OK;
+}
+
+static cudaError_t host_h2d(ces_handle_t h, double* dst, const double* src, int64_t rows, cudaStream_t s) {
+    const int64_t w = h->cols, ld = h->ldJ;       // host arrays are dense: ld = cols_local
+    if (rows < 1 || w < 1) return cudaSuccess;
+    if (ld == w) return cudaMemcpyAsync(dst, src, (size_t)rows * w * sizeof(double), cudaMemcpyHostToDevice, s);
+    return cudaMemcpy2DAsync(dst, ld * sizeof(double), src, w * sizeof(double), w * sizeof(double), rows, cudaMemcpyHostToDevice, s);
+}
+
+int ces_host_begin(ces_handle_t h, int rule, int formulation, const double* U, const double* G, const double* xi,
+                   int* nchunks_out, int64_t* bounds_out /* [5] */) {
+    CES_TRY(valid(h, true));
+    if (rule < CES_RULE_EKS || rule > CES_RULE_EKI) return fail(CES_ERR_INVALID, "unknown update rule %s%lld", "", rule);
+    if (formulation != CES_FORM_INTERACTION && formulation != CES_FORM_FACTORED) return fail(CES_ERR_INVALID, "unknown formulation%s", "");
+    if ((!U || !G) && h->cols > 0) return fail(CES_ERR_INVALID, "ces_host_begin: null pointer%s", "");
+    CES_TRY(host_staging(h));
+    const int64_t p = h->p, k = h->k, ld = h->ldJ, w = h->cols;
+    // ---- uploads, all on the copy stream, in the order the main stream needs them: G in row chunks, U, xi.
+    // Row means are per row over the particles, so a row chunk of G can be summed and centred as soon as it has
+    // landed, and the D GEMM of the first column panel (own block) contracts over the rows received so far (later chunks
+    // accumulate with beta = 1).  With chunks of k/32, 7k/32 and 3k/4 rows every upload after the first hides behind the
+    // GEMM of the previous chunk (per row of G the GEMM takes 2 J_l min(panel, J_l) flop at ~36 TF/s, the upload 8 J_l
+    // bytes at ~55 GB/s: a factor ~6 at a 16384-column panel), so the only exposed transfer is the first k/32 rows.
+    // Dense Gamma (W = Gamma^-1 R needs all of R), the factored formulation and small shapes use one chunk.
+    int nchunk = 1;
+    int64_t* bound = h->hb_bound;
+    bound[0] = 0; bound[1] = bound[2] = bound[3] = bound[4] = k;
+    if (formulation == CES_FORM_INTERACTION && h->gamma_diag && k >= 256 && h->Jl >= 2048) {
+        nchunk = 3;
+        bound[1] = round_up(k / 32, 16);
+        bound[2] = round_up(k / 4, 16);
+    }
+    h->hb_nchunk = nchunk;
+    h->hb_formulation = formulation;
+    h->hb_have_xi = xi != nullptr;
+    mark(h, "host:begin");
+    CES_CUDA(cudaEventRecord(h->start_ev, h->st));                // after the previous step's readers of the staging buffers
+    CES_CUDA(cudaStreamWaitEvent(h->copy_st, h->start_ev, 0));
+    static const char* up_names[4] = {"upload:G0", "upload:G1", "upload:G2", "upload:G3"};
+    for (int c = 0; c < nchunk; ++c) {
+        CES_CUDA(host_h2d(h, h->stage_G + bound[c] * ld, G + bound[c] * w, bound[c + 1] - bound[c], h->copy_st));
+        CES_CUDA(cudaEventRecord(h->g_ev[c], h->copy_st));
+        mark(h, up_names[c], h->copy_st);
+    }
+    CES_CUDA(host_h2d(h, h->stage_U, U, p, h->copy_st));
+    CES_CUDA(cudaEventRecord(h->u_ev, h->copy_st));
+    mark(h, "upload:U", h->copy_st);
+    if (xi) {
+        CES_CUDA(host_h2d(h, h->stage_xi, xi, p, h->copy_st));
         CES_CUDA(cudaEventRecord(h->copy_ev, h->copy_st));
+        mark(h, "upload:xi", h->copy_st);
     }
-    CES_CUDA(h2d(h->stage_U, U, p, h->st));
-    CES_CUDA(h2d(h->stage_G, G, k, h->st));
+    h->last_rule = rule;
+    if (nchunks_out) *nchunks_out = nchunk;
+    if (bounds_out) for (int i = 0; i < 5; ++i) bounds_out[i] = bound[i];
+    return CES_OK;
+}
+
+int ces_host_sums_g(ces_handle_t h, int chunk) {
+    CES_TRY(valid(h, true));
+    if (chunk < 0 || chunk >= h->hb_nchunk) return fail(CES_ERR_INVALID, "ces_host_sums_g: bad chunk%s", "");
+    const int64_t r0 = h->hb_bound[chunk], nr = h->hb_bound[chunk + 1] - r0;
+    CES_CUDA(cudaStreamWaitEvent(h->st, h->g_ev[chunk], 0));
+    if (h->cols == 0) { CES_CUDA(cudaMemsetAsync(h->sums + r0, 0, nr * sizeof(double), h->st)); return CES_OK; }
+    return row_sums(h->st, h->stage_G + r0 * h->ldJ, h->ldJ, nr, h->cols, h->sums + r0);
+}
+
+int ces_host_centre_g(ces_handle_t h, int chunk) {
+    CES_TRY(valid(h, true));
+    if (chunk < 0 || chunk >= h->hb_nchunk) return fail(CES_ERR_INVALID, "ces_host_centre_g: bad chunk%s", "");
+    const int64_t r0 = h->hb_bound[chunk], nr = h->hb_bound[chunk + 1] - r0;
+    CES_TRY(centre_g_rows(h, h->stage_G, h->ldJ, r0, nr));
+    if (h->hb_nchunk > 1) {
+        // own block, first column panel: contract over the rows received so far
+        static const char* ck[4] = {"centred:G0", "centred:G1", "centred:G2", "centred:G3"};
+        static const char* dk[4] = {"D0:chunk0", "D0:chunk1", "D0:chunk2", "D0:chunk3"};
+        InteractRange rg;
+        rg.c_begin = 0; rg.c_end = h->panel < h->Jl ? h->panel : h->Jl; rg.k_lo = r0; rg.k_hi = r0 + nr;
+        rg.do_v = false; rg.reset = (chunk == 0); rg.finish = false;
+        mark(h, ck[chunk]);
+        CES_TRY(interaction_loops(h, h->W, true, 0, 1, rg));
+        mark(h, dk[chunk]);
+    }
+    return CES_OK;
+}
+
+int ces_host_sums_u(ces_handle_t h) {
+    CES_TRY(valid(h, true));
+    CES_TRY(finish_g(h));
+    CES_CUDA(cudaStreamWaitEvent(h->st, h->u_ev, 0));
+    if (h->cols == 0) { CES_CUDA(cudaMemsetAsync(h->sums + h->k, 0, h->p * sizeof(double), h->st)); return CES_OK; }
+    return row_sums(h->st, h->stage_U, h->ldJ, h->p, h->cols, h->sums + h->k);
+}
+
+int ces_host_centre_u(ces_handle_t h) {
+    CES_TRY(valid(h, true));
+    CES_TRY(centre_u_all(h, h->last_rule, h->stage_U, h->ldJ));
+    mark(h, "centred:U+Cuu");
+    return CES_OK;
+}
+
+// Own block: what is left of it after the chunks of ces_host_centre_g (V of the first panel, the remaining panels), or
+// all of it (single chunk).  Also starts chol(C^uu) on the side stream, so C^uu must be final (all-reduced) by now.
+int ces_host_interact_own(ces_handle_t h) {
+    CES_TRY(valid(h, true));
+    const int rule = h->last_rule;
+    if (h->hb_formulation == CES_FORM_FACTORED) {
+        if (h->nranks != 1) return fail(CES_ERR_STATE, "host steps: the factored formulation is single-GPU here%s", "");
+        return interaction_phase(h, rule, CES_FORM_FACTORED);
+    }
+    CES_TRY(start_cholesky(h, rule));
+    const bool whole = (h->nranks == 1);          // single GPU: the own block is the whole interaction
+    if (h->hb_nchunk > 1) {
+        const int64_t panel0 = h->panel < h->Jl ? h->panel : h->Jl;
+        InteractRange rv;                         // V of the first panel, then the remaining panels as usual
+        rv.c_begin = 0; rv.c_end = panel0; rv.do_d = false; rv.reset = false; rv.finish = whole && (panel0 >= h->Jl);
+        CES_TRY(interaction_loops(h, h->W, true, 0, 1, rv));
+        mark(h, "V0");
+        if (panel0 < h->Jl) {
+            InteractRange rr;
+            rr.c_begin = panel0; rr.reset = false; rr.finish = whole;
+            CES_TRY(interaction_loops(h, h->W, true, 0, 1, rr));
+            mark(h, "panels:rest");
+        }
+        return CES_OK;
+    }
+    InteractRange all;
+    all.finish = whole;
+    return interaction_loops(h, h->W, true, 0, 1, all);
+}
+
+int ces_host_update(ces_handle_t h, int ts_kind, double fixed_h, double* Uout_host, double* hk_host, double* metrics_host) {
+    CES_TRY(valid(h, true));
+    if (!Uout_host && h->cols > 0) return fail(CES_ERR_INVALID, "ces_host_update: null output%s", "");
+    if (h->hb_have_xi) CES_CUDA(cudaStreamWaitEvent(h->st, h->copy_ev, 0));
+    // phase 4 downloads U_next (in column chunks, overlapped) and ends with a synchronisation (status + scalars)
+    h->pending_out = h->cols > 0 ? Uout_host : nullptr;
+    h->pending_rows = h->p;
+    const int s4 = ces_phase4_update(h, h->last_rule, ts_kind, fixed_h, h->stage_U, h->ldJ, h->hb_have_xi ? h->stage_xi : nullptr,
+                                     h->ldJ, h->stage_out, h->ldJ, hk_host, metrics_host);
+    h->pending_out = nullptr;
+    return s4;
+}
+
+int ces_step_host(ces_handle_t h, int rule, int ts_kind, double fixed_h, double switch_, int formulation, const double* U,
+                  const double* G, const double* xi, double* Uout, double* hk_host, double* metrics_host) {
+    CES_TRY(valid(h, true));
+    if (h->nranks != 1) return fail(CES_ERR_STATE, "ces_step_host is single-GPU; use the ces_host_* pieces with nranks > 1%s", "");
+    if (!U || !G || !Uout) return fail(CES_ERR_INVALID, "ces_step_host: null pointer%s", "");
+    const int64_t p = h->p, k = h->k, ld = h->ldJ;
+    const bool small = h->use_small && formulation == CES_FORM_INTERACTION && small_step_eligible(h->p, h->k, h->Jl);
     if (small) {
+        // tiny problems keep everything on one stream -- extra streams and events would cost more than the copies
+        CES_TRY(host_staging(h));
+        if (xi) CES_CUDA(host_h2d(h, h->stage_xi, xi, p, h->st));
+        CES_CUDA(host_h2d(h, h->stage_U, U, p, h->st));
+        CES_CUDA(host_h2d(h, h->stage_G, G, k, h->st));
         h->pending_out = Uout;
         h->pending_rows = p;
         const int s1 = ces_step(h, rule, ts_kind, fixed_h, switch_, formulation, h->stage_U, ld, h->stage_G, ld,
@@ -859,18 +1121,23 @@ int ces_step_host(ces_handle_t h, int rule, int ts_kind, double fixed_h, double 
         h->pending_out = nullptr;
         return s1;
     }
-    CES_TRY(ces_phase1_sums(h, h->stage_U, ld, h->stage_G, ld));
-    CES_TRY(ces_phase2_centre(h, rule, h->stage_U, ld, h->stage_G, ld));
-    CES_TRY(interaction_phase(h, rule, formulation));
+    int nchunk = 1;
+    CES_TRY(ces_host_begin(h, rule, formulation, U, G, xi, &nchunk, nullptr));
+    for (int c = 0; c < nchunk; ++c) {
+        CES_TRY(ces_host_sums_g(h, c));
+        CES_TRY(ces_host_centre_g(h, c));
+    }
+    CES_TRY(ces_host_sums_u(h));
+    CES_TRY(ces_host_centre_u(h));
+    CES_TRY(ces_host_interact_own(h));
     if (rule == CES_RULE_ALDI_CONSTANT) CES_TRY(ces_phase4a_drift(h, switch_));
-    if (xi) CES_CUDA(cudaStreamWaitEvent(h->st, h->copy_ev, 0));
-    // phase 4 ends with a stream synchronisation (status + scalars); queue the result copy before it
-    h->pending_out = Uout;
-    h->pending_rows = p;
-    int s4 = ces_phase4_update(h, rule, ts_kind, fixed_h, h->stage_U, ld, xi ? h->stage_xi : nullptr, ld, h->stage_out, ld,
-                               hk_host, metrics_host);
-    h->pending_out = nullptr;
-    CES_TRY(s4);
+    return ces_host_update(h, ts_kind, fixed_h, Uout, hk_host, metrics_host);
+}
+
+int ces_set_pending_output(ces_handle_t h, double* host_out) {
+    CES_TRY(valid(h, true));
+    h->pending_out = host_out;
+    h->pending_rows = h->p;
     return CES_OK;
 }
 
@@ -906,6 +1173,44 @@ int ces_forward_map(ces_handle_t h, int map_kind, const double* A, int64_t lda, 
         return banana_map(st, U, ldu, cols, params[0], params[1], G, ldg);
     }
     return fail(CES_ERR_INVALID, "ces_forward_map: unknown map kind %s%lld", "", map_kind);
+}
+
+int ces_timeline_enable(ces_handle_t h, int on) {
+    CES_TRY(valid(h, false));
+    for (auto& m : h->marks) h->mark_pool.push_back(m.second);
+    h->marks.clear();
+    h->timeline = on != 0;
+    return CES_OK;
+}
+
+int ces_timeline_mark(ces_handle_t h, const char* name) {
+    CES_TRY(valid(h, false));
+    mark(h, name ? name : "");
+    return CES_OK;
+}
+
+int ces_timeline_read(ces_handle_t h, char* names, int64_t names_cap, double* ms, int64_t ms_cap, int64_t* count) {
+    CES_TRY(valid(h, false));
+    CES_CUDA(cudaDeviceSynchronize());
+    int64_t n = 0;
+    size_t used = 0;
+    for (auto& m : h->marks) {
+        if (n >= ms_cap) break;
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, h->marks[0].second, m.second) != cudaSuccess) { cudaGetLastError(); t = -1.f; }
+        if (ms) ms[n] = t;
+        if (names && used + m.first.size() + 2 <= (size_t)names_cap) {
+            memcpy(names + used, m.first.c_str(), m.first.size());
+            used += m.first.size();
+            names[used++] = '\n';
+            names[used] = 0;
+        }
+        ++n;
+    }
+    if (count) *count = n;
+    for (auto& m : h->marks) h->mark_pool.push_back(m.second);
+    h->marks.clear();
+    return CES_OK;
 }
 
 int ces_profile_enable(ces_handle_t h, int on) {

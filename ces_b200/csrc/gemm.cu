@@ -30,6 +30,17 @@ static int launch_modes(cudaStream_t st, const GemmCall& c, const CUtensorMap& m
 
 int gemm_tiles(int M, int N) { return (int)(ceil_div(M, GEMM_BM) * ceil_div(N, GEMM_BN)); }
 
+int gemm_sm_count() {
+    static int sms_of[kMaxDevices] = {};
+    int& sms = sms_of[device_slot()];
+    if (!sms) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1)
+            sms = 148;
+    }
+    return sms;
+}
+
 int gemm(cudaStream_t st, const GemmCall& c) {
     if (c.M < 1 || c.N < 1 || c.K < 1 || !c.A || !c.B || !c.C) return fail(CES_ERR_INVALID, "gemm: bad shape or null operand%s", "");
     CUtensorMap ma, mb;
@@ -61,14 +72,7 @@ int gemm(cudaStream_t st, const GemmCall& c) {
     a.kblocks_per_split = 0;
     a.splitk_ws = nullptr;
     {
-        static int sms_of[kMaxDevices] = {};
-        int& sms = sms_of[device_slot()];
-        if (!sms) {
-            int dev = 0;
-            if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1)
-                sms = 148;
-        }
-        a.wave_ctas = sms;
+        a.wave_ctas = gemm_sm_count();
         static const int env_serp = []() { const char* e = std::getenv("CES_GEMM_SERPENTINE"); return e ? atoi(e) : -1; }();
         // default on: -23 % DRAM reads on the D GEMM (profiles/r01_gemm_raster_sweep.csv); CES_GEMM_SERPENTINE=0 disables
         if (env_serp != 0) a.flags |= GEMM_SERPENTINE_K;

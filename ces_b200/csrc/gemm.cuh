@@ -41,7 +41,7 @@ struct GemmArgs {
     long long ldc;
     double alpha, beta;
     const double* alpha_dev;   // optional device scalar multiplied into alpha
-    double* ssq_partials;      // optional: [tiles] per-CTA sum of (alpha*acc)^2 over in-range outputs
+    double* ssq_partials;      // optional: [tiles] per-CTA sum of squares of the stored outputs (alpha*acc + beta*C), in range
     double* splitk_ws;         // when set: raw partial products go to [split][M][N] (ld = N) for the reduce kernel
     int tiles_m, tiles_n, group_m;
     int kblocks_per_split, splits;
@@ -235,6 +235,18 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         const int m = m_base + ((A_MODE == 0) ? perm_kc(i, g) : perm_mc(i, g));
         if (m >= args.M) continue;
         double* row = out + (size_t)m * ldo;
+        // beta != 0: all of this row's old values are loaded before the first store (independent loads in flight;
+        // interleaved with the stores they would serialise on possible aliasing -- the epilogue is exposed, one CTA per SM)
+        double old[NJ][2];
+        if (!to_ws && beta != 0.0) {
+#pragma unroll
+            for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int n = n_base + ((B_MODE == 1) ? perm_kc(j, 2 * t + e) : perm_mc(j, 2 * t + e));
+                    old[j][e] = n < args.N ? __ldcs(row + n) : 0.0;
+                }
+        }
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
 #pragma unroll
@@ -245,8 +257,8 @@ gemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     row[n] = acc[i][j][e];
                 } else {
                     double v = alpha * acc[i][j][e];
-                    ssq += v * v;
-                    if (beta != 0.0) v += beta * row[n];
+                    if (beta != 0.0) v += beta * old[j][e];
+                    ssq += v * v;           // of the value stored: a contraction accumulated in chunks (beta = 1) sums the final D
                     row[n] = v;
                 }
             }

@@ -38,6 +38,7 @@ struct GemmCall {
 
 int gemm(cudaStream_t st, const GemmCall& c);
 int gemm_tiles(int M, int N);
+int gemm_sm_count();   // SMs of the current device = CTAs of one wave of the GEMM (one CTA per SM)
 
 // Device scalar block of a handle (doubles).
 enum StepScalars : int {

@@ -66,8 +66,10 @@ def run_phases(phases, buffer, comm, p, k, rule, resolve=None, formulation="inte
         def allreduce_slice(t, lo, hi, op=None):
             return None
 
+    mark = phases.get("mark", lambda name: None)      # per-phase timeline (Engine.timeline), no-op by default
     phases["sums"]()
     allreduce(buffer("sums") if comm is not None else None)
+    mark("allreduce:sums:done")
     phases["centre"]()
     if formulation == "factored":
         if resolve is not None:
@@ -83,6 +85,7 @@ def run_phases(phases, buffer, comm, p, k, rule, resolve=None, formulation="inte
         overlapped = False
         if comm is not None:
             allreduce(buffer("cuu"))
+            mark("allreduce:cuu:done")
             e_all, ut_all = buffer("e_all"), buffer("ut_all")
             e_own, ut_own = e_all[rank * k:(rank + 1) * k], ut_all[rank * p:(rank + 1) * p]
             if dist.get_backend(group) == "nccl" and resolve != "always" and "interact_own" in phases:
@@ -93,6 +96,7 @@ def run_phases(phases, buffer, comm, p, k, rule, resolve=None, formulation="inte
                 phases["interact_own"]()
                 for wk in works:
                     wk.wait()
+                mark("allgather:e,ut:waited")
                 phases["interact_rest"]()
                 overlapped = True
             else:
@@ -102,6 +106,7 @@ def run_phases(phases, buffer, comm, p, k, rule, resolve=None, formulation="inte
             phases["interact"](resolve == "always")
     if comm is not None:
         allreduce_slice(buffer("scalars"), 0, 5)
+        mark("allreduce:scalars:done")
     keep = False
     if resolve == "spectral":
         # hk = 1 / lambda_max(D) (ces/calibrate.py:249-251); lambda_max(D) = lambda_max(Gamma^-1 C^pp), see csrc/eig.cu
@@ -236,6 +241,24 @@ class Engine(object):
         _lib.check(self.lib.ces_profile_read(self.h, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(fl)))
         return ms.value, n.value, fl.value
 
+    def timeline(self, on=True):
+        """Record named CUDA events per phase (ces_timeline_*); ``timeline_read`` returns [(name, ms), ...]."""
+        _lib.check(self.lib.ces_timeline_enable(self.h, 1 if on else 0))
+        self._timeline_on = bool(on)
+
+    def mark(self, name):
+        if getattr(self, "_timeline_on", False):
+            _lib.check(self.lib.ces_timeline_mark(self.h, name.encode()))
+
+    def timeline_read(self):
+        cap = 4096
+        names = ctypes.create_string_buffer(64 * cap)
+        ms = (ctypes.c_double * cap)()
+        n = ctypes.c_int64()
+        _lib.check(self.lib.ces_timeline_read(self.h, names, 64 * cap, ms, cap, ctypes.byref(n)))
+        labels = names.value.decode().split("\n")
+        return [(labels[i] if i < len(labels) else "?", float(ms[i])) for i in range(n.value)]
+
     def normal_noise(self, rows, seed, step, out=None):
         """(rows, cols) standard normal noise for this rank's columns, generated on the device (ces_fill_normal);
         identical to the corresponding columns of a single-GPU draw with the same (seed, step)."""
@@ -329,6 +352,7 @@ class Engine(object):
                 "finish_factored": lambda: _lib.check(lib.ces_phase3f_finish(h, r)),
                 "drift": lambda: _lib.check(lib.ces_phase4a_drift(h, float(switch))),
                 "update": update,
+                "mark": self.mark,
             }
             comm = (self.dist, self.group, self.rank) if self.nranks > 1 else None
             run_phases(phases, self.buffer, comm, self.p, self.k, rule, resolve, formulation)
@@ -383,14 +407,61 @@ class Engine(object):
         return self._views[key]
 
     def _step_host_sharded(self, rule, U, G, xi, fixed_h, switch, resolve, formulation):
-        """Column shard on host arrays: H2D of (U, G, xi) shards on a copy stream -- xi is needed only by the last
-        phase, so its upload overlaps the interaction GEMMs --, the phases with their collectives, D2H of the shard of
-        U_next into page-locked memory."""
-        torch = self.torch
+        """Column shard on host arrays.  Default rule set (no re-solve of D, interaction formulation): the pipelined
+        pieces of the library's host step (include/ces_b200.h) with this rank's collectives in between -- G uploads in
+        row chunks while the chunks already on the device are summed (all-reduce of that slice of the means), centred and
+        contracted into the own block's first D panel; U and xi follow behind; U_next comes back in overlapped column
+        chunks.  Other modes: plain uploads, then the device-pointer phases."""
+        torch, lib, h, dist, group = self.torch, self.lib, self.h, self.dist, self.group
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        G = np.ascontiguousarray(G, dtype=np.float64)
+        assert U.shape == (self.p, self.cols) and G.shape == (self.k, self.cols), (U.shape, G.shape, self.cols)
+        if xi is not None:
+            xi = np.ascontiguousarray(xi, dtype=np.float64)
+            assert xi.shape == U.shape
+        host = torch.empty((self.p, self.cols), dtype=torch.float64, pin_memory=self.p * self.cols * 8 >= (1 << 20))
+        ptr = lambda a: (_lib.host_ptr(a) if a is not None and a.size else None)
         with self.on_stream():
-            U = np.ascontiguousarray(U, dtype=np.float64)
-            G = np.ascontiguousarray(G, dtype=np.float64)
-            assert U.shape == (self.p, self.cols) and G.shape == (self.k, self.cols), (U.shape, G.shape, self.cols)
+            if resolve is None and formulation == "interaction":
+                r = _lib.RULES[rule]
+                ts = _lib.TS_FIXED if fixed_h is not None else _lib.TS_FROBENIUS
+                nch, bounds = ctypes.c_int(), (ctypes.c_int64 * 5)()
+                _lib.check(lib.ces_host_begin(h, r, 0, ptr(U), ptr(G), ptr(xi), ctypes.byref(nch), bounds))
+                sums, k, p = self.buffer("sums"), self.k, self.p
+                for c in range(nch.value):
+                    _lib.check(lib.ces_host_sums_g(h, c))
+                    dist.all_reduce(sums[0, bounds[c]:bounds[c + 1]], group=group)
+                    _lib.check(lib.ces_host_centre_g(h, c))
+                _lib.check(lib.ces_host_sums_u(h))
+                dist.all_reduce(sums[0, k:k + p], group=group)
+                _lib.check(lib.ces_host_centre_u(h))
+                dist.all_reduce(self.buffer("cuu"), group=group)
+                self.mark("allreduce:cuu:done")
+                e_all, ut_all = self.buffer("e_all"), self.buffer("ut_all")
+                e_own, ut_own = e_all[self.rank * k:(self.rank + 1) * k], ut_all[self.rank * p:(self.rank + 1) * p]
+                if dist.get_backend(group) == "nccl":
+                    works = [dist.all_gather_into_tensor(e_all, e_own, group=group, async_op=True),
+                             dist.all_gather_into_tensor(ut_all, ut_own, group=group, async_op=True)]
+                    _lib.check(lib.ces_host_interact_own(h))
+                    for wk in works:
+                        wk.wait()
+                else:
+                    dist.all_gather_into_tensor(e_all, e_own.clone(), group=group)
+                    dist.all_gather_into_tensor(ut_all, ut_own.clone(), group=group)
+                    _lib.check(lib.ces_host_interact_own(h))
+                self.mark("allgather:e,ut:waited")
+                _lib.check(lib.ces_phase3_blocks(h, r, 1, self.nranks - 1))
+                scal = self.buffer("scalars")
+                dist.all_reduce(scal[0, 0:5], group=group)
+                self.mark("allreduce:scalars:done")
+                if rule == "aldi_constant":
+                    _lib.check(lib.ces_phase4a_drift(h, float(switch)))
+                    dist.all_reduce(scal[0, 5:6], op=dist.ReduceOp.MAX, group=group)
+                _lib.check(lib.ces_host_update(h, ts, float(fixed_h) if fixed_h is not None else 0.0,
+                                               host.data_ptr() if self.cols else None, ctypes.byref(self._hk), self._met))
+                met = {key: float(self._met[i]) for i, key in enumerate(_METRIC_KEYS)}
+                return host.numpy(), float(self._hk.value), met
+            # ---- non-default modes: plain uploads (xi on a side stream: only the last phase needs it), device phases
             if "h2d" not in self._views:
                 self._views["h2d"] = torch.cuda.Stream()
                 for name, rows in (("U", self.p), ("G", self.k), ("xi", self.p), ("out", self.p)):
@@ -403,16 +474,17 @@ class Engine(object):
             Gd.copy_(torch.from_numpy(G), non_blocking=True)
             xi_ready = None
             if xi is not None:
-                xi = np.ascontiguousarray(xi, dtype=np.float64)
-                assert xi.shape == U.shape
                 with torch.cuda.stream(copy_st):
                     Xd.copy_(torch.from_numpy(xi), non_blocking=True)
                     xi_ready = torch.cuda.Event()
                     xi_ready.record(copy_st)
             self._xi_ready = xi_ready
-            out, hk, met = self._step(rule, Ud, Gd, Xd if xi is not None else None, Od, fixed_h, switch, resolve, formulation)
-            host = torch.empty((self.p, self.cols), dtype=torch.float64, pin_memory=self.p * self.cols * 8 >= (1 << 20))
-            host.copy_(out, non_blocking=True)
+            # the last phase downloads U_next itself, in column chunks overlapped with their assembly
+            _lib.check(lib.ces_set_pending_output(h, host.data_ptr() if self.cols else None))
+            try:
+                out, hk, met = self._step(rule, Ud, Gd, Xd if xi is not None else None, Od, fixed_h, switch, resolve, formulation)
+            finally:
+                lib.ces_set_pending_output(h, None)
             main.synchronize()
             return host.numpy(), hk, met
 

@@ -139,10 +139,46 @@ int ces_step(ces_handle_t h, int rule, int ts_kind, double fixed_h, double switc
              double* Uout_dev, int64_t ldo, double* hk_host, double* metrics_host);
 
 /* The same step on HOST buffers (dense, ld = J): host->device copies of U, G, xi and the device->host
- * copy of U_out happen inside the call.  This is the call behind sampling.eks_update*(numpy arrays). */
+ * copy of U_out happen inside the call.  This is the call behind sampling.eks_update*(numpy arrays)
+ * (ces/calibrate.py:418, 451, 492).  The copies are pipelined against the arithmetic: G is uploaded in row chunks on a
+ * copy stream, each chunk is summed and centred as it lands and the first column panel of D = (1/J) E^T W accumulates
+ * over the rows received so far, U and xi follow behind; U_next is downloaded in column chunks while the next chunk is
+ * still being assembled.  (Page-locked host buffers make the copies asynchronous; pageable ones still work.) */
 int ces_step_host(ces_handle_t h, int rule, int ts_kind, double fixed_h, double switch_, int formulation,
                   const double* U_host, const double* G_host, const double* xi_host, double* Uout_host,
                   double* hk_host, double* metrics_host);
+/* Per-phase timeline (profiles/): while enabled, the phases record named CUDA events on the streams they use
+ * (ces_timeline_mark adds one on the handle's main stream, e.g. around a collective the host issues).
+ * ces_timeline_read synchronises the device, returns the marks recorded since the last read as '\n'-separated names
+ * and their times in ms relative to the first mark (-1: not comparable), and clears them. */
+int ces_timeline_enable(ces_handle_t h, int on);
+int ces_timeline_mark(ces_handle_t h, const char* name);
+int ces_timeline_read(ces_handle_t h, char* names, int64_t names_cap, double* ms, int64_t ms_cap, int64_t* count);
+/* The host step in pieces, for column-sharded callers (nranks > 1; ces_step_host is exactly this sequence with no
+ * collectives).  Host arrays are this rank's dense shards: U_host, xi_host p x cols_local, G_host k x cols_local.
+ *   ces_host_begin         queues every upload on the copy stream (G in *nchunks row chunks with bounds[0..nchunks],
+ *                          then U, then xi) and returns at once
+ *   for c in chunks:       ces_host_sums_g(c)     row sums of the chunk          [all-reduce "sums"[bounds[c]:bounds[c+1]]]
+ *                          ces_host_centre_g(c)   E, W rows; with several chunks also the own block's first D panel,
+ *                                                 contracted over these rows (accumulating)
+ *   ces_host_sums_u        z, data-space diagnostics; row sums of U                   [all-reduce "sums"[k:k+p]]
+ *   ces_host_centre_u      U~, Z, diagnostics, local C^uu                             [all-reduce "cuu"; all-gather "e_all", "ut_all"]
+ *   ces_host_interact_own  starts chol(C^uu); the rest of the own block (runs while the gathers are in flight)
+ *   [ces_phase3_blocks(h, rule, 1, nranks - 1)]                                       [all-reduce "scalars"[0:5]]
+ *   [ces_phase4a_drift for aldi_constant                                              all-reduce(max) "scalars"[5:6]]
+ *   ces_host_update        waits for xi, assembles U_next and downloads this rank's p x cols_local block into
+ *                          Uout_host in overlapped column chunks; returns hk and the diagnostics like ces_phase4_update */
+int ces_host_begin(ces_handle_t h, int rule, int formulation, const double* U_host, const double* G_host,
+                   const double* xi_host, int* nchunks_out, int64_t* bounds_out /* [5] */);
+int ces_host_sums_g(ces_handle_t h, int chunk);
+int ces_host_centre_g(ces_handle_t h, int chunk);
+int ces_host_sums_u(ces_handle_t h);
+int ces_host_centre_u(ces_handle_t h);
+int ces_host_interact_own(ces_handle_t h);
+int ces_host_update(ces_handle_t h, int ts_kind, double fixed_h, double* Uout_host, double* hk_host, double* metrics_host);
+/* Device-pointer phases with a host destination: the next ces_phase4_update also copies this rank's p x cols_local
+ * block of U_next to host_out (dense, ld = cols_local; column chunks overlapped with the assembly).  One-shot; NULL cancels. */
+int ces_set_pending_output(ces_handle_t h, double* host_out);
 
 /* Batched forward map G[:, j] = model(U[:, j]) for this rank's columns (enka.G_ens, ces/calibrate.py:106-130).
  * CES_MAP_LINEAL / _LOG: A_dev is k x p (ld = lda, even, 16-byte aligned), b_dev is k doubles or NULL.

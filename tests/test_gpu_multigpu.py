@@ -35,7 +35,7 @@ def _worker(rank, world, port, rule, d, k, J, q):
         from ces_b200.engine import Engine
         from oracle import eks_oracle as eo, forward_oracle as fo
 
-        pr = eo.linear_gaussian_problem(d, k, J, dense_gamma=True)
+        pr = eo.linear_gaussian_problem(d, k, J, dense_gamma=(k < 256))     # the pipelined host step needs a diagonal Gamma
         eng = Engine(d, k, J, group=dist.group.WORLD)
         eng.set_problem(pr["y"], pr["Gamma"], pr["Sigma0"], pr["mu"], pr["ustar"])
         sl = slice(eng.col_lo, eng.col_hi)
@@ -59,15 +59,31 @@ def _worker(rank, world, port, rule, d, k, J, q):
                         np.random.normal(0, 1, [d, J]), t_last=t)
             U, t = o["Uk"], o["t"]
         rerr = float(np.abs(s.Ustar - U).max() / np.abs(U).max())
-        q.put((rank, err, float(herr), float(merr), rerr, s.Uall.shape))
+        # the reference-facing single update on host arrays with a process group: every rank passes the full arrays
+        # (the reference's calling convention; the full U_next comes back on every rank), or its own column shard
+        s2 = calibrate.sampling(d, k, J)
+        s2.mu, s2.sigma, s2.ustar, s2.group = pr["mu"], pr["Sigma0"], pr["ustar"], dist.group.WORLD
+        fn = getattr(s2, {"eks": "eks_update", "aldi": "eks_update_aldi", "aldi_constant": "eks_update_aldi_constant"}[rule])
+        Uf = fn(pr["y"], pr["U0"], pr["G"], pr["Gamma"], 0, xi=pr["xi"])
+        Ul = fn(pr["y"], pr["U0"][:, sl], pr["G"][:, sl], pr["Gamma"], 0, xi=pr["xi"][:, sl], local_shard=True)
+        hosterr = max(float(np.abs(Uf - ref["Uk"]).max()), float(np.abs(Ul - ref["Uk"][:, sl]).max()) if Ul.size else 0.0) \
+            / float(np.abs(ref["Uk"]).max())
+        assert Uf.shape == (d, J) and Ul.shape == (d, sl.stop - sl.start) and len(s2.metrics["t"]) == 2
+        # device noise on odd shard widths / offsets (J = 301 on 2 ranks): every rank can draw, no rank raises
+        xi_dev = s2._engine.normal_noise(d, seed=3, step=1)
+        assert xi_dev.shape == (d, sl.stop - sl.start)
+        q.put((rank, max(err, hosterr), float(herr), float(merr), rerr, s.Uall.shape))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,rule,J", [(2, "aldi", 301), (2, "aldi_constant", 256), (2, "eks", 130), (4, "aldi", 1030),
-                                          (4, "eks", 515), (3, "aldi_constant", 700)])
-def test_multi_gpu_step_matches_oracle(world, rule, J):
-    """world >= 3 exercises the batched launches over the other ranks' source blocks (rotated order with wrap-around)."""
+@pytest.mark.parametrize("world,rule,J,d,k", [(2, "aldi", 301, 24, 40), (2, "aldi_constant", 256, 24, 40), (2, "eks", 130, 24, 40),
+                                              (4, "aldi", 1030, 24, 40), (4, "eks", 515, 24, 40),
+                                              (3, "aldi_constant", 700, 24, 40), (2, "aldi", 4300, 16, 272)])
+def test_multi_gpu_step_matches_oracle(world, rule, J, d, k):
+    """world >= 3 exercises the batched launches over the other ranks' source blocks (rotated order with wrap-around);
+    the last case (k >= 256, shards of >= 2048 particles) takes the pipelined host step: G uploaded in row chunks, the
+    means all-reduced slice by slice, the own block's first D panel accumulated over the chunks."""
     import torch.multiprocessing as mp
 
     if torch.cuda.device_count() < world:
@@ -75,7 +91,7 @@ def test_multi_gpu_step_matches_oracle(world, rule, J):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, rule, 24, 40, J, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, rule, d, k, J, q)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
@@ -83,7 +99,7 @@ def test_multi_gpu_step_matches_oracle(world, rule, J):
         assert p.exitcode == 0
     for rank, err, herr, merr, rerr, shape in sorted(q.get(timeout=10) for _ in range(world)):
         assert err < 1e-10 and herr < 1e-10 and merr < 1e-10, (rank, err, herr, merr)
-        assert rerr < 1e-9 and shape == (4, 24, J)
+        assert rerr < 1e-9 and shape == (4, d, J)
 
 
 def _worker_more(rank, world, port, q):

@@ -76,6 +76,35 @@ def test_step_parity_against_oracle(d, k, J, dense):
         eng.close()
 
 
+def test_pipelined_host_step_panels_and_chunked_download():
+    """ces_step_host on a shape that takes every pipelined branch: G uploaded in three row chunks with the first column
+    panel of D accumulated over them (beta = 1, sum of squares from the stored values), several D panels (small
+    d_panel_bytes), ragged J, and U_next downloaded in column chunks on the second stream.  Against the oracle, and
+    against the device-resident step on the same inputs."""
+    d, k, J = 24, 272, 4300
+    pr = eo.linear_gaussian_problem(d, k, J)
+    eng = Engine(d, k, J, d_panel_bytes=1536 * 8 * 4304)
+    try:
+        eng.set_problem(pr["y"], pr["Gamma"], pr["Sigma0"], pr["mu"], pr["ustar"])
+        dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        for rule in RULES + ("eki",):
+            xi = pr["xi"] if rule != "eki" else None
+            o = eo.step(rule, pr["y"], pr["U0"], pr["G"], pr["Gamma"], pr["mu"], pr["Sigma0"], pr["ustar"], pr["xi"])
+            Uk, hk, met = eng.step_host(rule, pr["U0"], pr["G"], xi)
+            assert _rel(Uk, o["Uk"]) < TOL and abs(hk - o["hk"]) <= TOL * o["hk"], rule
+            for key in met:
+                assert abs(met[key] - o["metrics"][key]) <= TOL * abs(o["metrics"][key]), (rule, key)
+            Ud, hd, _ = eng.step(rule, dev(pr["U0"]), dev(pr["G"]), dev(xi) if xi is not None else None)
+            assert _rel(Uk, Ud.cpu().numpy()) < 1e-12 and abs(hk - hd) <= 1e-13 * hd, rule
+        # pageable and page-locked host arrays give the same result
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+        U2, h2, _ = eng.step_host("aldi", pin(pr["U0"]), pin(pr["G"]), pin(pr["xi"]))
+        U1, h1, _ = eng.step_host("aldi", pr["U0"], pr["G"], pr["xi"])
+        assert np.array_equal(U1, U2) and h1 == h2
+    finally:
+        eng.close()
+
+
 @pytest.mark.parametrize("d,k,J,dense", [(6, 9, 40, True), (20, 33, 150, False), (64, 130, 600, True)])
 def test_non_default_time_steps_match_oracle(d, k, J, dense):
     """time_step='constant' / 'mix' with the hk C^pp + Gamma re-solve of D (ces/calibrate.py:439-441, 470-473)
