@@ -28,7 +28,8 @@ EXPORTS = (
     "ces_fill_normal", "ces_phase3_blocks", "ces_frobenius", "ces_phase3d_spectral", "ces_lorenz63_forward",
     "ces_lorenz96_forward", "ces_set_pending_output", "ces_timeline_enable",
     "ces_timeline_mark", "ces_timeline_read", "ces_host_begin", "ces_host_sums_g", "ces_host_centre_g", "ces_host_sums_u",
-    "ces_host_centre_u", "ces_host_interact_own", "ces_host_update",
+    "ces_host_centre_u", "ces_host_interact_own", "ces_host_update", "ces_ipc_export", "ces_ipc_import", "ces_peer_gather",
+    "ces_peer_gather_wait", "ces_host_interact_chunk",
 )
 
 _i64, _int, _dbl, _vp = ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_void_p
@@ -78,9 +79,14 @@ def load():
     lib.ces_step_host.argtypes = [_vp, _int, _int, _dbl, _dbl, _int, _dp, _dp, _dp, _dp,
                                   ctypes.POINTER(_dbl), ctypes.POINTER(_dbl)]
     lib.ces_set_pending_output.argtypes = [_vp, _dp]
+    lib.ces_ipc_export.argtypes = [_vp, ctypes.c_char_p, ctypes.c_char_p]
+    lib.ces_ipc_import.argtypes = [_vp, _int, ctypes.c_char_p, ctypes.c_char_p]
+    lib.ces_peer_gather.argtypes = [_vp]
+    lib.ces_peer_gather_wait.argtypes = [_vp]
     lib.ces_host_begin.argtypes = [_vp, _int, _int, _dp, _dp, _dp, ctypes.POINTER(_int), ctypes.POINTER(_i64)]
     lib.ces_host_sums_g.argtypes = [_vp, _int]
-    lib.ces_host_centre_g.argtypes = [_vp, _int]
+    lib.ces_host_centre_g.argtypes = [_vp, _int, _int]
+    lib.ces_host_interact_chunk.argtypes = [_vp, _int]
     lib.ces_host_sums_u.argtypes = [_vp]
     lib.ces_host_centre_u.argtypes = [_vp]
     lib.ces_host_interact_own.argtypes = [_vp]

@@ -43,6 +43,11 @@ struct ces_handle_s {
     double *stage_U = nullptr, *stage_G = nullptr, *stage_xi = nullptr, *stage_out = nullptr;
     double* pending_out = nullptr;      // host destination of stage_out, copied inside phase 4 before its final sync
     int64_t pending_rows = 0;
+    // gathers of the other ranks' E / U~ blocks by copy engines over NVLink (ces_ipc_*, ces_peer_gather): IPC-mapped bases
+    // of every peer's E_all / Ut_all, a stream for the pulls, an event each way
+    std::vector<double*> peer_E, peer_Ut;
+    cudaStream_t gather_st = nullptr;
+    cudaEvent_t gather_go = nullptr, gather_done = nullptr;
     int hb_nchunk = 1, hb_formulation = 0;   // state of a host step in progress (ces_host_begin ... ces_host_update)
     bool hb_have_xi = false;
     int64_t hb_bound[5] = {0, 0, 0, 0, 0};
@@ -249,6 +254,11 @@ int ces_destroy(ces_handle_t h) {
     for (cudaEvent_t e : h->out_ev) if (e) cudaEventDestroy(e);
     if (h->copy_st) cudaStreamDestroy(h->copy_st);
     if (h->out_st) { cudaStreamSynchronize(h->out_st); cudaStreamDestroy(h->out_st); }
+    if (h->gather_st) { cudaStreamSynchronize(h->gather_st); cudaStreamDestroy(h->gather_st); }
+    if (h->gather_go) cudaEventDestroy(h->gather_go);
+    if (h->gather_done) cudaEventDestroy(h->gather_done);
+    for (double* q : h->peer_E) if (q) cudaIpcCloseMemHandle(q);
+    for (double* q : h->peer_Ut) if (q) cudaIpcCloseMemHandle(q);
     if (h->hS) cudaFreeHost(h->hS);
     delete h;
     cudaGetLastError();
@@ -1024,11 +1034,23 @@ int ces_host_sums_g(ces_handle_t h, int chunk) {
     return row_sums(h->st, h->stage_G + r0 * h->ldJ, h->ldJ, nr, h->cols, h->sums + r0);
 }
 
-int ces_host_centre_g(ces_handle_t h, int chunk) {
+int ces_host_interact_chunk(ces_handle_t h, int chunk);
+
+int ces_host_centre_g(ces_handle_t h, int chunk, int interact) {
     CES_TRY(valid(h, true));
     if (chunk < 0 || chunk >= h->hb_nchunk) return fail(CES_ERR_INVALID, "ces_host_centre_g: bad chunk%s", "");
     const int64_t r0 = h->hb_bound[chunk], nr = h->hb_bound[chunk + 1] - r0;
     CES_TRY(centre_g_rows(h, h->stage_G, h->ldJ, r0, nr));
+    if (interact) return ces_host_interact_chunk(h, chunk);
+    return CES_OK;
+}
+
+// Own block, first column panel: contract over the rows of this chunk (no-op with a single chunk: ces_host_interact_own
+// then does the whole block).  Chunks must be taken in order.
+int ces_host_interact_chunk(ces_handle_t h, int chunk) {
+    CES_TRY(valid(h, true));
+    if (chunk < 0 || chunk >= h->hb_nchunk) return fail(CES_ERR_INVALID, "ces_host_interact_chunk: bad chunk%s", "");
+    const int64_t r0 = h->hb_bound[chunk], nr = h->hb_bound[chunk + 1] - r0;
     if (h->hb_nchunk > 1) {
         // own block, first column panel: contract over the rows received so far
         static const char* ck[4] = {"centred:G0", "centred:G1", "centred:G2", "centred:G3"};
@@ -1125,7 +1147,7 @@ int ces_step_host(ces_handle_t h, int rule, int ts_kind, double fixed_h, double 
     CES_TRY(ces_host_begin(h, rule, formulation, U, G, xi, &nchunk, nullptr));
     for (int c = 0; c < nchunk; ++c) {
         CES_TRY(ces_host_sums_g(h, c));
-        CES_TRY(ces_host_centre_g(h, c));
+        CES_TRY(ces_host_centre_g(h, c, 1));
     }
     CES_TRY(ces_host_sums_u(h));
     CES_TRY(ces_host_centre_u(h));
@@ -1173,6 +1195,72 @@ int ces_forward_map(ces_handle_t h, int map_kind, const double* A, int64_t lda, 
         return banana_map(st, U, ldu, cols, params[0], params[1], G, ldg);
     }
     return fail(CES_ERR_INVALID, "ces_forward_map: unknown map kind %s%lld", "", map_kind);
+}
+
+// ---- gathers over peer memory (one process per GPU, all on one NVSwitch domain) ---------------------------------
+// Every rank exports its E_all / Ut_all allocations as CUDA IPC handles, the host exchanges the 64-byte handles once
+// (torch.distributed all_gather_object) and every rank maps its peers' buffers.  Per step, after the collective that
+// follows the centring (the all-reduce of C^uu: when it has completed on this rank's stream, every peer has written
+// its own E / U~ block), ces_peer_gather queues one device-to-device copy per peer and buffer on a side stream --
+// copy engines over NVLink, no SM is taken from the own-block GEMMs that run meanwhile, unlike an NCCL all-gather --
+// and ces_peer_gather_wait makes the main stream wait for them.  A peer overwrites its block only in the next step's
+// centring, which is ordered after the all-reduce of the step scalars, which every rank enters only after its GEMMs
+// on the pulled blocks: no further handshake is needed.
+int ces_ipc_export(ces_handle_t h, void* e_handle, void* ut_handle) {
+    CES_TRY(valid(h, false));
+    if (h->forward_only || !e_handle || !ut_handle) return fail(CES_ERR_INVALID, "ces_ipc_export: bad argument%s", "");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CES_CUDA(cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t*>(e_handle), h->E_all));
+    CES_CUDA(cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t*>(ut_handle), h->Ut_all));
+    return CES_OK;
+}
+
+int ces_ipc_import(ces_handle_t h, int peer, const void* e_handle, const void* ut_handle) {
+    CES_TRY(valid(h, false));
+    if (h->forward_only || peer < 0 || peer >= h->nranks || peer == h->rank || !e_handle || !ut_handle)
+        return fail(CES_ERR_INVALID, "ces_ipc_import: bad argument%s", "");
+    if (h->peer_E.empty()) { h->peer_E.assign(h->nranks, nullptr); h->peer_Ut.assign(h->nranks, nullptr); }
+    void *pe = nullptr, *pu = nullptr;
+    cudaIpcMemHandle_t he, hu;
+    memcpy(&he, e_handle, 64);
+    memcpy(&hu, ut_handle, 64);
+    CES_CUDA(cudaIpcOpenMemHandle(&pe, he, cudaIpcMemLazyEnablePeerAccess));
+    CES_CUDA(cudaIpcOpenMemHandle(&pu, hu, cudaIpcMemLazyEnablePeerAccess));
+    h->peer_E[peer] = static_cast<double*>(pe);
+    h->peer_Ut[peer] = static_cast<double*>(pu);
+    return CES_OK;
+}
+
+int ces_peer_gather(ces_handle_t h) {
+    CES_TRY(valid(h, true));
+    if (h->nranks < 2) return CES_OK;
+    if ((int)h->peer_E.size() != h->nranks) return fail(CES_ERR_STATE, "ces_peer_gather: peers were not imported%s", "");
+    if (!h->gather_st) {
+        CES_CUDA(cudaStreamCreateWithFlags(&h->gather_st, cudaStreamNonBlocking));
+        CES_CUDA(cudaEventCreateWithFlags(&h->gather_go, cudaEventDisableTiming));
+        CES_CUDA(cudaEventCreateWithFlags(&h->gather_done, cudaEventDisableTiming));
+    }
+    CES_CUDA(cudaEventRecord(h->gather_go, h->st));
+    CES_CUDA(cudaStreamWaitEvent(h->gather_st, h->gather_go, 0));
+    const size_t eb = (size_t)h->k * h->ldJ, ub = (size_t)h->p * h->ldJ;
+    // rotated order: at any moment every peer is read by a different rank; E first (the D GEMMs need it first)
+    for (int pass = 0; pass < 2; ++pass)
+        for (int i = 1; i < h->nranks; ++i) {
+            const int s = (h->rank + i) % h->nranks;
+            if (!h->peer_E[s] || !h->peer_Ut[s]) return fail(CES_ERR_STATE, "ces_peer_gather: peer %s%lld was not imported", "", s);
+            if (pass == 0) CES_CUDA(cudaMemcpyAsync(h->E_all + s * eb, h->peer_E[s] + s * eb, eb * sizeof(double), cudaMemcpyDeviceToDevice, h->gather_st));
+            else CES_CUDA(cudaMemcpyAsync(h->Ut_all + s * ub, h->peer_Ut[s] + s * ub, ub * sizeof(double), cudaMemcpyDeviceToDevice, h->gather_st));
+        }
+    CES_CUDA(cudaEventRecord(h->gather_done, h->gather_st));
+    mark(h, "peer_gather:done", h->gather_st);
+    return CES_OK;
+}
+
+int ces_peer_gather_wait(ces_handle_t h) {
+    CES_TRY(valid(h, true));
+    if (h->nranks < 2 || !h->gather_done) return CES_OK;
+    CES_CUDA(cudaStreamWaitEvent(h->st, h->gather_done, 0));
+    return CES_OK;
 }
 
 int ces_timeline_enable(ces_handle_t h, int on) {

@@ -7,6 +7,7 @@ when the ensemble is sharded by particle columns over several GPUs
 """
 import contextlib
 import ctypes
+import os
 
 import numpy as np
 
@@ -88,7 +89,17 @@ def run_phases(phases, buffer, comm, p, k, rule, resolve=None, formulation="inte
             mark("allreduce:cuu:done")
             e_all, ut_all = buffer("e_all"), buffer("ut_all")
             e_own, ut_own = e_all[rank * k:(rank + 1) * k], ut_all[rank * p:(rank + 1) * p]
-            if dist.get_backend(group) == "nccl" and resolve != "always" and "interact_own" in phases:
+            if "peer_gather" in phases and resolve != "always" and "interact_own" in phases:
+                # the other ranks' blocks are pulled by copy engines over NVLink (ces_peer_gather: peers mapped through
+                # CUDA IPC) while the D / V GEMMs of this rank's own block run with every SM; the all-reduce of C^uu
+                # just queued is the cross-rank ordering the pulls need
+                phases["peer_gather"]()
+                phases["interact_own"]()
+                phases["peer_wait"]()
+                mark("peer_gather:waited")
+                phases["interact_rest"]()
+                overlapped = True
+            elif dist.get_backend(group) == "nccl" and resolve != "always" and "interact_own" in phases:
                 # NCCL: in-place all-gathers started asynchronously; the D / V GEMMs of this rank's own block (already
                 # in place after the centring phase) run while the other ranks' blocks arrive over NVLink
                 works = [dist.all_gather_into_tensor(e_all, e_own, group=group, async_op=True),
@@ -99,6 +110,9 @@ def run_phases(phases, buffer, comm, p, k, rule, resolve=None, formulation="inte
                 mark("allgather:e,ut:waited")
                 phases["interact_rest"]()
                 overlapped = True
+            elif "peer_gather" in phases:
+                phases["peer_gather"]()
+                phases["peer_wait"]()
             else:
                 dist.all_gather_into_tensor(e_all, e_own.clone(), group=group)
                 dist.all_gather_into_tensor(ut_all, ut_own.clone(), group=group)
@@ -195,6 +209,38 @@ class Engine(object):
         self._views = {}
         self._hk = ctypes.c_double()
         self._met = (ctypes.c_double * 4)()
+        self.peer_gather = False
+        if (self.nranks > 1 and int(d_panel_bytes) >= 0 and os.environ.get("CES_PEER_GATHER", "1") != "0"
+                and self.dist.get_backend(group) == "nccl"):
+            self.peer_gather = self._setup_peer_gather()
+
+    def _setup_peer_gather(self):
+        """Map every peer's E / U~ buffers through CUDA IPC (ces_ipc_*), so the per-step gathers run as copy-engine
+        copies over NVLink instead of an NCCL all-gather.  All ranks must agree: if the mapping fails anywhere (ranks on
+        different nodes, IPC unavailable) everybody keeps the NCCL path."""
+        torch, dist = self.torch, self.dist
+        ok = 1
+        try:
+            he, hu = ctypes.create_string_buffer(64), ctypes.create_string_buffer(64)
+            _lib.check(self.lib.ces_ipc_export(self.h, he, hu))
+            mine = (self.rank, he.raw, hu.raw)
+        except Exception:
+            ok, mine = 0, (self.rank, None, None)
+        everyone = [None] * self.nranks
+        dist.all_gather_object(everyone, mine, group=self.group)
+        if ok:
+            try:
+                for rank, e_raw, u_raw in everyone:
+                    if rank == self.rank:
+                        continue
+                    if e_raw is None:
+                        raise RuntimeError("peer %d exported nothing" % rank)
+                    _lib.check(self.lib.ces_ipc_import(self.h, int(rank), e_raw, u_raw))
+            except Exception:
+                ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        return bool(flag.item())
 
     def on_stream(self):
         return stream_guard(self.torch, self.stream)
@@ -354,6 +400,9 @@ class Engine(object):
                 "update": update,
                 "mark": self.mark,
             }
+            if self.peer_gather:
+                phases["peer_gather"] = lambda: _lib.check(lib.ces_peer_gather(h))
+                phases["peer_wait"] = lambda: _lib.check(lib.ces_peer_gather_wait(h))
             comm = (self.dist, self.group, self.rank) if self.nranks > 1 else None
             run_phases(phases, self.buffer, comm, self.p, self.k, rule, resolve, formulation)
         met = {key: float(self._met[i]) for i, key in enumerate(_METRIC_KEYS)}
@@ -428,10 +477,13 @@ class Engine(object):
                 nch, bounds = ctypes.c_int(), (ctypes.c_int64 * 5)()
                 _lib.check(lib.ces_host_begin(h, r, 0, ptr(U), ptr(G), ptr(xi), ctypes.byref(nch), bounds))
                 sums, k, p = self.buffer("sums"), self.k, self.p
+                last = nch.value - 1
                 for c in range(nch.value):
                     _lib.check(lib.ces_host_sums_g(h, c))
                     dist.all_reduce(sums[0, bounds[c]:bounds[c + 1]], group=group)
-                    _lib.check(lib.ces_host_centre_g(h, c))
+                    # the last chunk's share of the own block's D panel is deferred until the gathers of the other
+                    # ranks' blocks have been started: they then run under it instead of after it
+                    _lib.check(lib.ces_host_centre_g(h, c, 0 if c == last else 1))
                 _lib.check(lib.ces_host_sums_u(h))
                 dist.all_reduce(sums[0, k:k + p], group=group)
                 _lib.check(lib.ces_host_centre_u(h))
@@ -439,17 +491,24 @@ class Engine(object):
                 self.mark("allreduce:cuu:done")
                 e_all, ut_all = self.buffer("e_all"), self.buffer("ut_all")
                 e_own, ut_own = e_all[self.rank * k:(self.rank + 1) * k], ut_all[self.rank * p:(self.rank + 1) * p]
-                if dist.get_backend(group) == "nccl":
+                if self.peer_gather:
+                    _lib.check(lib.ces_peer_gather(h))
+                    _lib.check(lib.ces_host_interact_chunk(h, last))
+                    _lib.check(lib.ces_host_interact_own(h))
+                    _lib.check(lib.ces_peer_gather_wait(h))
+                elif dist.get_backend(group) == "nccl":
                     works = [dist.all_gather_into_tensor(e_all, e_own, group=group, async_op=True),
                              dist.all_gather_into_tensor(ut_all, ut_own, group=group, async_op=True)]
+                    _lib.check(lib.ces_host_interact_chunk(h, last))
                     _lib.check(lib.ces_host_interact_own(h))
                     for wk in works:
                         wk.wait()
                 else:
                     dist.all_gather_into_tensor(e_all, e_own.clone(), group=group)
                     dist.all_gather_into_tensor(ut_all, ut_own.clone(), group=group)
+                    _lib.check(lib.ces_host_interact_chunk(h, last))
                     _lib.check(lib.ces_host_interact_own(h))
-                self.mark("allgather:e,ut:waited")
+                self.mark("gather:e,ut:waited")
                 _lib.check(lib.ces_phase3_blocks(h, r, 1, self.nranks - 1))
                 scal = self.buffer("scalars")
                 dist.all_reduce(scal[0, 0:5], group=group)

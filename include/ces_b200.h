@@ -147,6 +147,16 @@ int ces_step(ces_handle_t h, int rule, int ts_kind, double fixed_h, double switc
 int ces_step_host(ces_handle_t h, int rule, int ts_kind, double fixed_h, double switch_, int formulation,
                   const double* U_host, const double* G_host, const double* xi_host, double* Uout_host,
                   double* hk_host, double* metrics_host);
+/* Gathers of the other ranks' E / U~ blocks over peer memory instead of an NCCL all-gather (one process per GPU on one
+ * NVSwitch domain): ces_ipc_export writes the 64-byte CUDA IPC handles of this rank's "e_all" / "ut_all" buffers, the
+ * host exchanges them once and calls ces_ipc_import for every peer.  Per step, after the all-reduce of "cuu" has been
+ * queued, ces_peer_gather queues one device-to-device copy per peer block on a side stream (copy engines over NVLink:
+ * no SM is taken from the own-block GEMMs that run meanwhile), and ces_peer_gather_wait makes the handle's stream wait
+ * for them before ces_phase3_blocks(h, rule, 1, nranks - 1).  See csrc/api.cu for why no further handshake is needed. */
+int ces_ipc_export(ces_handle_t h, void* e_handle /* 64 bytes */, void* ut_handle /* 64 bytes */);
+int ces_ipc_import(ces_handle_t h, int peer_rank, const void* e_handle, const void* ut_handle);
+int ces_peer_gather(ces_handle_t h);
+int ces_peer_gather_wait(ces_handle_t h);
 /* Per-phase timeline (profiles/): while enabled, the phases record named CUDA events on the streams they use
  * (ces_timeline_mark adds one on the handle's main stream, e.g. around a collective the host issues).
  * ces_timeline_read synchronises the device, returns the marks recorded since the last read as '\n'-separated names
@@ -159,8 +169,10 @@ int ces_timeline_read(ces_handle_t h, char* names, int64_t names_cap, double* ms
  *   ces_host_begin         queues every upload on the copy stream (G in *nchunks row chunks with bounds[0..nchunks],
  *                          then U, then xi) and returns at once
  *   for c in chunks:       ces_host_sums_g(c)     row sums of the chunk          [all-reduce "sums"[bounds[c]:bounds[c+1]]]
- *                          ces_host_centre_g(c)   E, W rows; with several chunks also the own block's first D panel,
- *                                                 contracted over these rows (accumulating)
+ *                          ces_host_centre_g(c, interact)   E, W rows; interact != 0: ces_host_interact_chunk(c) at once
+ *                          ces_host_interact_chunk(c)       with several chunks: the own block's first D panel contracted
+ *                                                 over these rows (accumulating; chunks in order).  A sharded caller defers
+ *                                                 the last chunk's until the gathers of E / U~ have been started
  *   ces_host_sums_u        z, data-space diagnostics; row sums of U                   [all-reduce "sums"[k:k+p]]
  *   ces_host_centre_u      U~, Z, diagnostics, local C^uu                             [all-reduce "cuu"; all-gather "e_all", "ut_all"]
  *   ces_host_interact_own  starts chol(C^uu); the rest of the own block (runs while the gathers are in flight)
@@ -171,7 +183,8 @@ int ces_timeline_read(ces_handle_t h, char* names, int64_t names_cap, double* ms
 int ces_host_begin(ces_handle_t h, int rule, int formulation, const double* U_host, const double* G_host,
                    const double* xi_host, int* nchunks_out, int64_t* bounds_out /* [5] */);
 int ces_host_sums_g(ces_handle_t h, int chunk);
-int ces_host_centre_g(ces_handle_t h, int chunk);
+int ces_host_centre_g(ces_handle_t h, int chunk, int interact);
+int ces_host_interact_chunk(ces_handle_t h, int chunk);
 int ces_host_sums_u(ces_handle_t h);
 int ces_host_centre_u(ces_handle_t h);
 int ces_host_interact_own(ces_handle_t h);
