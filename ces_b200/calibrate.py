@@ -79,6 +79,44 @@ def _identity(a):
     return (id(a), a.__array_interface__['data'][0], a.shape, a.strides, a.dtype.str)
 
 
+class _HostTrace(object):
+    """Device -> host copies of the per-iteration ensembles that do not stall the loop (``trace`` / ``save_online`` of
+    ``sampling.run``).  ``push`` queues an asynchronous copy into fresh page-locked memory on a side
+    stream and returns a ticket; ``get`` waits for that copy only.  ``run`` asks for iteration i's arrays while iteration
+    i + 1 is already computing (online save) or at the very end (trace), so the forward solves and updates never wait
+    for PCIe.  The source tensors are kept alive until their copy has completed."""
+
+    SMALL = 1 << 18         # below 256 KB a plain synchronous copy is cheaper than a page-locked buffer and two events
+
+    def __init__(self, torch):
+        self.torch = torch
+        self.stream = None
+        self.items = []
+
+    def push(self, dev_tensor):
+        torch = self.torch
+        if dev_tensor.numel() * dev_tensor.element_size() < self.SMALL:
+            self.items.append((dev_tensor.cpu(), None, None))
+            return len(self.items) - 1
+        if self.stream is None:
+            self.stream = torch.cuda.Stream()
+        host = torch.empty(dev_tensor.shape, dtype=dev_tensor.dtype, pin_memory=True)
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            host.copy_(dev_tensor, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        self.items.append((host, done, dev_tensor))
+        return len(self.items) - 1
+
+    def get(self, ticket):
+        host, done, _ = self.items[ticket]
+        if done is not None:
+            done.synchronize()
+            self.items[ticket] = (host, None, None)
+        return host.numpy()
+
+
 class enka(object):
     """State holder of an ensemble Kalman run.  ces/calibrate.py:12-237."""
 
@@ -144,14 +182,18 @@ class enka(object):
             padded = np.empty((theta.shape[0], width))
             padded[:, :n] = theta
             padded[:, n:] = theta[:, -1:]
-            eng = Engine(theta.shape[0], self.n_obs, width, d_panel_bytes=-1)       # forward maps only
-            try:
-                U = torch.from_numpy(padded).cuda()
-                G = torch.empty(self.n_obs, width, dtype=torch.float64, device="cuda")
-                model.evaluate_ensemble(eng, U, G)
-                return G[:, :n].cpu().numpy()
-            finally:
-                eng.close()
+            # forward-only handle, kept between calls of the same shape
+            key = (theta.shape[0], int(self.n_obs), width, torch.cuda.current_device())
+            cache = getattr(self, "_forward_cache", None)
+            if cache is None or cache[0] != key:
+                if cache is not None:
+                    cache[1].close()
+                cache = (key, Engine(theta.shape[0], self.n_obs, width, d_panel_bytes=-1))
+                self._forward_cache = cache
+            U = torch.from_numpy(padded).cuda()
+            G = torch.empty(self.n_obs, width, dtype=torch.float64, device="cuda")
+            model.evaluate_ensemble(cache[1], U, G)
+            return G[:, :n].cpu().numpy()
         return self._host_G_ens(theta, model)
 
     def _host_G_ens(self, theta, model):
@@ -230,6 +272,7 @@ class enka(object):
     def load(self, path='./', eks_dir='ces/', ix_ensemble=False, flag_metrics=False):
         """Rebuild ``Uall, Gall, Ustar, Gstar, J, metrics`` from a directory written by ``save``."""
         where = path + eks_dir
+        os.listdir(where)               # FileNotFoundError for a missing directory, like the reference (:203)
         try:
             with open(where + 'metrics.pkl', 'rb') as fh:
                 self.metrics = pickle.load(fh)
@@ -575,23 +618,55 @@ class sampling(enka):
             G_dev.copy_(torch.from_numpy(np.ascontiguousarray(G_host[:self.n_obs])))
             return G_dev, G_host
 
-        def gather_host(local, rows):
-            """Full (rows, J) host array from the column shards."""
+        def gather_dev(local, rows, private=True):
+            """Full (rows, J) DEVICE tensor from the column shards; single GPU: the tensor itself, or a private copy when
+            the caller will overwrite it before an asynchronous reader is done (the forward-output buffer)."""
             if eng.nranks == 1:
-                return local.cpu().numpy()
+                big = local.numel() * 8 >= _HostTrace.SMALL
+                return local.clone() if (private and big) else local
             parts = [torch.empty(rows, eng.Jl, dtype=torch.float64, device=dev) for _ in range(eng.nranks)]
             padded = torch.zeros(rows, eng.Jl, dtype=torch.float64, device=dev)
             padded[:, :hi - lo] = local
             eng.dist.all_gather(parts, padded, group=group)
-            full = torch.cat(parts, dim=1)[:, :J]
-            return full.cpu().numpy()
+            return torch.cat(parts, dim=1)[:, :J].contiguous()
+
+        def gather_host(local, rows):
+            """Full (rows, J) host array from the column shards (synchronous)."""
+            return gather_dev(local, rows, private=False).cpu().numpy()
+
+        # trace / save_online: asynchronous device->host copies into page-locked memory (no stall of the loop); the
+        # arrays of iteration i are materialised when iteration i + 1 has been queued (online save) or after the loop
+        host_trace = _HostTrace(torch) if (trace or save_online) else None
+        tickets = []                    # per iteration: (U ticket | array, G ticket | array)
+        saved_upto = [0]
+
+        def flush_online(upto):
+            """np.save the iterations [saved_upto, upto) whose copies were queued earlier (ces/calibrate.py:371-385)."""
+            if not (save_online and eng.rank == 0):
+                return
+            tag = model.model_name + '-eks-' + str(getattr(model, 'l_window', 0)).zfill(3) + '-' + str(self.J).zfill(4)
+            if hasattr(self, 'nexp'):
+                tag += '-' + str(self.nexp).zfill(2)
+            where = self.directory + '/ensembles/' + tag + '/'
+            try:
+                os.makedirs(where)
+            except OSError:
+                pass
+            for it in range(saved_upto[0], upto):
+                tu, tg = tickets[it]
+                Uh = host_trace.get(tu) if isinstance(tu, int) else tu
+                Gh = host_trace.get(tg) if isinstance(tg, int) else tg
+                np.save(where + 'ensemble_' + str(it).zfill(4), Uh)
+                np.save(where + 'Gensemble_' + str(it).zfill(4), Gh)
+            saved_upto[0] = max(saved_upto[0], upto)
 
         for i in range(self.T):
             G_cur, G_host = forward(U_dev)
-            if trace:
-                self.Uall.append(gather_host(U_dev, self.p))
-                self.Gall.append(G_host if (G_host is not None and (eng.nranks == 1 or is_pde))
-                                 else gather_host(G_cur, self.n_obs))
+            if host_trace is not None:
+                tu = host_trace.push(gather_dev(U_dev, self.p, private=False))     # every update returns a new tensor
+                tg = (G_host if (G_host is not None and (eng.nranks == 1 or is_pde))
+                      else host_trace.push(gather_dev(G_cur, self.n_obs)))
+                tickets.append((tu, tg))
             if known:
                 setattr(self, 'update_rule', {'eks': 'eks_update', 'aldi': 'eks_update_linear',
                                               'aldi_constant': 'eks_update_aldi', 'eki': 'eki_update'}[rule])
@@ -614,14 +689,27 @@ class sampling(enka):
             # an unknown ``update`` leaves the ensemble unchanged and records nothing, like :364-369 --
             # the reference then fails on the empty ``metrics['t']``; so do we
             if save_online:
-                # the reference reads model.l_window here (:375-376), which its own Darcy model lacks; default it
-                tag = model.model_name + '-eks-' + str(getattr(model, 'l_window', 0)).zfill(3) + '-' + str(self.J).zfill(4)
-                if hasattr(self, 'nexp'):
-                    tag += '-' + str(self.nexp).zfill(2)
+                # same files as enka.save(online=True, counter=i) (:371-385; the reference reads model.l_window there,
+                # which its own Darcy model lacks: defaulted to 0).  Iteration i - 1 is written now, while iteration i's
+                # copies are still in flight; metrics.pkl follows the latest completed update like the reference's
+                flush_online(i)
                 if eng.rank == 0:
-                    self.save(path=self.directory + '/ensembles/', file=tag + '/', online=True, counter=i)
+                    tag = model.model_name + '-eks-' + str(getattr(model, 'l_window', 0)).zfill(3) + '-' + str(self.J).zfill(4)
+                    if hasattr(self, 'nexp'):
+                        tag += '-' + str(self.nexp).zfill(2)
+                    try:
+                        os.makedirs(self.directory + '/ensembles/' + tag + '/')
+                    except OSError:
+                        pass
+                    with open(self.directory + '/ensembles/' + tag + '/metrics.pkl', "wb") as fh:
+                        pickle.dump(self.metrics, fh)
             if self.metrics['t'][-1] > kwargs.get('t_tol', 2.):
                 break
+        flush_online(len(tickets))
+        if trace:
+            for tu, tg in tickets:
+                self.Uall.append(host_trace.get(tu) if isinstance(tu, int) else tu)
+                self.Gall.append(host_trace.get(tg) if isinstance(tg, int) else tg)
 
         G_cur, G_host = forward(U_dev, final=True)
         U_fin = gather_host(U_dev, self.p)

@@ -48,6 +48,8 @@ struct ces_handle_s {
     std::vector<double*> peer_E, peer_Ut;
     cudaStream_t gather_st = nullptr;
     cudaEvent_t gather_go = nullptr, gather_done = nullptr;
+    double* run_ws = nullptr;           // ces_small_run: trace / noise / scalars of a whole run
+    int64_t run_ws_len = 0;
     int hb_nchunk = 1, hb_formulation = 0;   // state of a host step in progress (ces_host_begin ... ces_host_update)
     bool hb_have_xi = false;
     int64_t hb_bound[5] = {0, 0, 0, 0, 0};
@@ -241,6 +243,7 @@ int ces_destroy(ces_handle_t h) {
     if (h->aux_st) cudaStreamSynchronize(h->aux_st);
     if (h->copy_st) cudaStreamSynchronize(h->copy_st);
     for (void* ptr : h->allocs) cudaFree(ptr);
+    if (h->run_ws) cudaFree(h->run_ws);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     for (auto& m : h->marks) cudaEventDestroy(m.second);
     for (cudaEvent_t e : h->mark_pool) cudaEventDestroy(e);
@@ -1160,6 +1163,72 @@ int ces_set_pending_output(ces_handle_t h, double* host_out) {
     CES_TRY(valid(h, true));
     h->pending_out = host_out;
     h->pending_rows = h->p;
+    return CES_OK;
+}
+
+// The whole run loop of a small single-GPU problem in one launch (csrc/small.cu: small_run_kernel).
+int ces_small_run(ces_handle_t h, int rule, int ts_kind, double fixed_h, double switch_, int map_kind, const double* A_dev,
+                  int64_t lda, const double* b_dev, const double* params_host, const double* U0_host, const double* xi_host,
+                  uint64_t seed, uint64_t step0, int64_t T, double t0, int have_t0, double t_tol, double* Utrace_host,
+                  double* Gtrace_host, double* S_host, double* t_host, int64_t* nsteps_host) {
+    CES_TRY(valid(h, true));
+    if (h->nranks != 1) return fail(CES_ERR_STATE, "ces_small_run is single-GPU%s", "");
+    const int64_t p = h->p, k = h->k, J = h->Jl;
+    if (!small_step_eligible(p, k, J)) return fail(CES_ERR_INVALID, "ces_small_run: the problem is too large for the single-CTA path%s", "");
+    if (rule < CES_RULE_EKS || rule > CES_RULE_EKI) return fail(CES_ERR_INVALID, "unknown update rule %s%lld", "", rule);
+    if (ts_kind != CES_TS_FROBENIUS && ts_kind != CES_TS_FIXED) return fail(CES_ERR_INVALID, "unknown step-size rule%s", "");
+    if (T < 1 || !U0_host || !Utrace_host || !Gtrace_host || !S_host || !t_host || !nsteps_host)
+        return fail(CES_ERR_INVALID, "ces_small_run: bad argument%s", "");
+    if (map_kind < CES_MAP_LINEAL || map_kind > CES_MAP_BANANA) return fail(CES_ERR_INVALID, "ces_small_run: unknown map kind%s", "");
+    if ((map_kind == CES_MAP_LINEAL || map_kind == CES_MAP_LINEAL_LOG) ? !A_dev : (!params_host || p != 2 || k != 2))
+        return fail(CES_ERR_INVALID, "ces_small_run: the map needs A (lineal) or two parameters with p = k = 2%s", "");
+    cudaStream_t st = h->st;
+    const int64_t nu = (T + 1) * p * J, ng = (T + 1) * k * J, nx = (rule == CES_RULE_EKI) ? 0 : T * p * J;
+    const int64_t total = nu + ng + nx + T * S_COUNT + T + 2;
+    if (h->run_ws_len < total) {
+        if (h->run_ws) cudaFree(h->run_ws);
+        h->run_ws = nullptr; h->run_ws_len = 0;
+        if (cudaMalloc(&h->run_ws, (size_t)total * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return fail(CES_ERR_NOMEM, "ces_small_run: workspace allocation failed%s", ""); }
+        h->run_ws_len = total;
+    }
+    double* Ut = h->run_ws;
+    double* Gt = Ut + nu;
+    double* Xi = Gt + ng;
+    double* Sall = Xi + nx;
+    double* tv = Sall + T * S_COUNT;
+    int* nst = reinterpret_cast<int*>(tv + T);
+    CES_CUDA(cudaMemcpyAsync(Ut, U0_host, (size_t)p * J * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (nx > 0) {
+        if (xi_host) CES_CUDA(cudaMemcpyAsync(Xi, xi_host, (size_t)nx * sizeof(double), cudaMemcpyHostToDevice, st));
+        else for (int64_t it = 0; it < T; ++it) CES_TRY(fill_normal(st, Xi + it * p * J, J, p, J, 0, seed, step0 + (uint64_t)it));
+    }
+    SmallStepCall c;
+    c.p = p; c.k = k; c.J = J; c.rule = rule; c.ts_kind = ts_kind; c.fixed_h = fixed_h; c.switch_ = switch_;
+    c.U = nullptr; c.G = nullptr; c.xi = nullptr; c.ldu = c.ldg = c.ldxi = c.ldo = J; c.out = nullptr;
+    c.y = h->y; c.mu = h->mu; c.ustar = h->ustar; c.bprior = h->bprior;
+    c.ginv_diag = h->gamma_diag ? h->ginv_diag : nullptr; c.Ginv = h->gamma_diag ? nullptr : h->Ginv;
+    c.sinv_diag = h->sinv_diag; c.sig_diag = h->sig_diag;
+    c.Sinv = h->sigma_diag ? nullptr : h->Sinv; c.Sigma0 = h->sigma_diag ? nullptr : h->Sigma0;
+    c.ldk = h->ldk; c.ldp = h->ldp; c.S = nullptr;
+    SmallRunCall rc;
+    rc.T = T; rc.map_kind = map_kind; rc.have_t0 = have_t0; rc.t0 = t0; rc.t_tol = t_tol;
+    rc.A = A_dev; rc.lda = lda; rc.b = b_dev;
+    rc.par0 = params_host ? params_host[0] : 0.0; rc.par1 = params_host ? params_host[1] : 0.0;
+    rc.Utrace = Ut; rc.Gtrace = Gt; rc.Xi = nx > 0 ? Xi : nullptr; rc.Sall = Sall; rc.tvec = tv; rc.nsteps = nst;
+    h->last_rule = rule;
+    CES_TRY(small_run(st, c, rc));
+    int n = 0;
+    CES_CUDA(cudaMemcpyAsync(&n, nst, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CES_CUDA(cudaStreamSynchronize(st));
+    if (n < 1 || n > T) return fail(CES_ERR_CUDA, "ces_small_run: kernel failure%s", "");
+    CES_CUDA(cudaMemcpyAsync(Utrace_host, Ut, (size_t)(n + 1) * p * J * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CES_CUDA(cudaMemcpyAsync(Gtrace_host, Gt, (size_t)(n + 1) * k * J * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CES_CUDA(cudaMemcpyAsync(S_host, Sall, (size_t)n * S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CES_CUDA(cudaMemcpyAsync(t_host, tv, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CES_CUDA(cudaStreamSynchronize(st));
+    *nsteps_host = n;
+    const double info = S_host[(size_t)(n - 1) * S_COUNT + S_INFO];
+    if (info != 0.0) return fail(CES_ERR_NOT_SPD, "%s: matrix is not positive definite (pivot %lld)", "cov(U)", (long long)info);
     return CES_OK;
 }
 

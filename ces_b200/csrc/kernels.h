@@ -119,6 +119,19 @@ struct SmallStepCall {
 };
 bool small_step_eligible(int64_t p, int64_t k, int64_t J);
 int small_step(cudaStream_t st, const SmallStepCall& c);
+// the whole run loop (forward map + update per iteration, stopping rule) of a small problem in one launch
+struct SmallRunCall {
+    int64_t T;
+    int map_kind, have_t0;
+    double t0, t_tol;
+    const double* A; int64_t lda; const double* b;
+    double par0, par1;
+    double *Utrace, *Gtrace;
+    const double* Xi;
+    double *Sall, *tvec;
+    int* nsteps;
+};
+int small_run(cudaStream_t st, const SmallStepCall& c, const SmallRunCall& rc);
 
 // forward.cu
 int exp_map(cudaStream_t st, const double* X, int64_t ldx, int64_t rows, int64_t cols, double* out, int64_t ldo);

@@ -43,8 +43,9 @@ __device__ __forceinline__ void block_reduce5(double (&v)[5], double (*scratch)[
     }
 }
 
-__global__ void __launch_bounds__(512, 1) small_step_kernel(const SmallArgs a) {
-    extern __shared__ double sm[];
+// One update by the whole CTA (one thread per particle).  Every thread of the CTA must call it (barriers inside); it
+// returns with the new column written to a.out and the step scalars in a.S (thread 0), without a trailing barrier.
+__device__ __forceinline__ void small_step_body(const SmallArgs& a, double* sm, double (*scratch)[32]) {
     const int p = a.p, k = a.k, J = a.J;
     double* Es = sm;                    // k x J   E = G - mean
     double* Uts = Es + (size_t)k * J;   // p x J   U~ = U - mean
@@ -54,7 +55,6 @@ __global__ void __launch_bounds__(512, 1) small_step_kernel(const SmallArgs a) {
     double* Ms = Ls + SP * SP;          // p x p   chol(Sigma0 + h C)   (eks)
     double* cb = Ms + SP * SP;          // p       C Sigma0^-1 mu       (eks)
     double* sc = cb + SP;               // scalars: h, sqrt2h
-    __shared__ double scratch[5][32];
     const int j = threadIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
     const bool on = j < J;
 
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(512, 1) small_step_kernel(const SmallArgs a) {
             }
     }
     __syncthreads();
-    if (!on) return;
+    if (!on) return;                    // (no barrier follows inside this function)
 
     // ---- assemble U_{n+1}[:, j]
     const double h = sc[0], s2h = sc[1];
@@ -287,6 +287,94 @@ __global__ void __launch_bounds__(512, 1) small_step_kernel(const SmallArgs a) {
     for (int q = 0; q < SP; ++q) if (q < p) a.out[(size_t)q * a.ldo + j] = o[q];
 }
 
+__global__ void __launch_bounds__(512, 1) small_step_kernel(const SmallArgs a) {
+    extern __shared__ double sm[];
+    __shared__ double scratch[5][32];
+    small_step_body(a, sm, scratch);
+}
+
+// ---- the whole sampling.run loop of a small problem in ONE launch (BASELINE config 1: d = 2, k = 10, J = 100, T = 1000).
+// Per iteration (ces/calibrate.py:341-388): forward map of every particle (enka.G_ens, :351-352; the ces.utils maps),
+// update (small_step_body), cumulative pseudo-time (:262-265) and the stopping rule t > t_tol (:387-388).  The chain of
+// ensembles IS the trace: iteration i reads U from slot i of Utrace and writes slot i + 1, the forward outputs go to
+// Gtrace, the step scalars of every iteration to Sall -- the host downloads them once at the end.  No launch, no host
+// round trip and no PCIe transfer happens between iterations.
+struct SmallRunArgs {
+    SmallArgs base;                     // problem data, rule, step-size rule (U / G / xi / out / S are set per iteration)
+    int T, map_kind, have_t0;
+    double t0, t_tol;
+    const double* A; long long lda;     // lineal / lineal_log: k x p (ld = lda), b: k or nullptr
+    const double* b;
+    double par0, par1;                  // elliptic (x1, x2) / banana (a, b)
+    double* Utrace;                     // (T + 1) x p x J
+    double* Gtrace;                     // (T + 1) x k x J
+    const double* Xi;                   // T x p x J
+    double* Sall;                       // T x S_COUNT
+    double* tvec;                       // T cumulative times
+    int* nsteps;                        // [0]: updates performed
+};
+
+__device__ __forceinline__ void small_forward(const SmallRunArgs& r, const double* U, double* G, int j) {
+    const int p = r.base.p, k = r.base.k, J = r.base.J;
+    if (r.map_kind == CES_MAP_LINEAL || r.map_kind == CES_MAP_LINEAL_LOG) {
+        double u[SP];
+#pragma unroll
+        for (int q = 0; q < SP; ++q) {
+            u[q] = q < p ? U[(size_t)q * J + j] : 0.0;
+            if (r.map_kind == CES_MAP_LINEAL_LOG && q < p) u[q] = exp(u[q]);
+        }
+        for (int m = 0; m < k; ++m) {
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < SP; ++q) if (q < p) s = fma(r.A[(size_t)m * r.lda + q], u[q], s);
+            G[(size_t)m * J + j] = r.b ? s + r.b[m] : s;
+        }
+    } else if (r.map_kind == CES_MAP_ELLIPTIC) {
+        const double u1 = U[j], u2 = U[J + j], e = exp(-u1), x1 = r.par0, x2 = r.par1;
+        G[j] = (u2 * x1) + (e * (-x1 * x1 + x1) * 0.5);
+        G[J + j] = (u2 * x2) + (e * (-x2 * x2 + x2) * 0.5);
+    } else {                            // banana
+        const double u1 = U[j], u2 = U[J + j];
+        G[j] = u1 * r.par0;
+        G[J + j] = u2 / r.par0 - r.par1 * (u1 * u1 + r.par0 * r.par0);
+    }
+}
+
+__global__ void __launch_bounds__(512, 1) small_run_kernel(const SmallRunArgs r) {
+    extern __shared__ double sm[];
+    __shared__ double scratch[5][32];
+    __shared__ double t_acc;
+    __shared__ int stop;
+    const int p = r.base.p, k = r.base.k, J = r.base.J;
+    const int j = threadIdx.x;
+    const bool on = j < J;
+    if (j == 0) { t_acc = r.t0; stop = 0; }
+    int it = 0;
+    for (; it < r.T; ++it) {
+        const double* Ucur = r.Utrace + (size_t)it * p * J;
+        double* Gcur = r.Gtrace + (size_t)it * k * J;
+        if (on) small_forward(r, Ucur, Gcur, j);            // own column: read back by the same thread below
+        SmallArgs a = r.base;
+        a.U = Ucur; a.ldu = J; a.G = Gcur; a.ldg = J;
+        a.xi = r.Xi ? r.Xi + (size_t)it * p * J : nullptr; a.ldxi = J;
+        a.out = r.Utrace + (size_t)(it + 1) * p * J; a.ldo = J;
+        a.S = r.Sall + (size_t)it * S_COUNT;
+        small_step_body(a, sm, scratch);
+        __syncthreads();                                    // every column of slot it + 1 is written, a.S is complete
+        if (j == 0) {
+            const double h = a.S[S_H];
+            t_acc = (it == 0 && !r.have_t0) ? h : t_acc + h;    // ces/calibrate.py:262-265
+            r.tvec[it] = t_acc;
+            if (t_acc > r.t_tol || a.S[S_INFO] != 0.0 || !(h == h)) stop = 1;    // :387-388; failed pivot / NaN: the host raises
+        }
+        __syncthreads();
+        if (stop) { ++it; break; }
+    }
+    // the final forward evaluation of the last ensemble (:390-398)
+    if (on) small_forward(r, r.Utrace + (size_t)it * p * J, r.Gtrace + (size_t)it * k * J, j);
+    if (j == 0) r.nsteps[0] = it;
+}
+
 bool small_step_eligible(int64_t p, int64_t k, int64_t J) {
     return p <= SMALL_P_MAX && k <= SMALL_K_MAX && J <= 512 && J >= 2;
 }
@@ -310,6 +398,32 @@ int small_step(cudaStream_t st, const SmallStepCall& c) {
         configured = smem;
     }
     small_step_kernel<<<1, threads, smem, st>>>(a);
+    CES_LAUNCHED(1);
+    return CES_OK;
+}
+
+int small_run(cudaStream_t st, const SmallStepCall& c, const SmallRunCall& rc) {
+    SmallRunArgs r;
+    SmallArgs& a = r.base;
+    a.p = (int)c.p; a.k = (int)c.k; a.J = (int)c.J; a.rule = c.rule; a.ts_kind = c.ts_kind;
+    a.fixed_h = c.fixed_h; a.switch_ = c.switch_;
+    a.U = nullptr; a.G = nullptr; a.xi = nullptr; a.ldu = a.ldg = a.ldxi = a.ldo = c.J; a.out = nullptr;
+    a.y = c.y; a.mu = c.mu; a.ustar = c.ustar; a.bprior = c.bprior;
+    a.ginv_diag = c.ginv_diag; a.Ginv = c.Ginv; a.sinv_diag = c.sinv_diag; a.sig_diag = c.sig_diag;
+    a.Sinv = c.Sinv; a.Sigma0 = c.Sigma0; a.ldk = c.ldk; a.ldp = c.ldp;
+    a.S = nullptr;
+    r.T = (int)rc.T; r.map_kind = rc.map_kind; r.have_t0 = rc.have_t0; r.t0 = rc.t0; r.t_tol = rc.t_tol;
+    r.A = rc.A; r.lda = rc.lda; r.b = rc.b; r.par0 = rc.par0; r.par1 = rc.par1;
+    r.Utrace = rc.Utrace; r.Gtrace = rc.Gtrace; r.Xi = rc.Xi; r.Sall = rc.Sall; r.tvec = rc.tvec; r.nsteps = rc.nsteps;
+    const int threads = (int)round_up(c.J, 32);
+    const size_t smem = ((size_t)(c.k + c.p) * c.J + (SK + SP) + 3 * SP * SP + SP + 8) * sizeof(double);
+    static size_t configured_of[kMaxDevices] = {};
+    size_t& configured = configured_of[device_slot()];
+    if (smem > 48 * 1024 && smem > configured) {
+        CES_CUDA(cudaFuncSetAttribute(small_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    small_run_kernel<<<1, threads, smem, st>>>(r);
     CES_LAUNCHED(1);
     return CES_OK;
 }

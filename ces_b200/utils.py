@@ -24,6 +24,14 @@ class _DeviceMap(object):
         """(A_dev, lda, b_dev, params) for ces_forward_map."""
         return None, 0, None, None
 
+    def __getstate__(self):
+        # device handles and buffers do not travel (joblib pickles the model when enka.parallel is set); they are rebuilt
+        state = dict(self.__dict__)
+        state.pop("_single_cache", None)
+        if "_dev" in state:
+            state["_dev"] = None
+        return state
+
     def evaluate_ensemble(self, engine, U_dev, G_dev):
         A, lda, b, params = self._device_args(engine.torch)
         return engine.forward_map(self.device_kind, U_dev, G_dev, A=A, lda=lda, b=b, params=params)
@@ -34,15 +42,23 @@ class _DeviceMap(object):
 
         theta = np.asarray(theta, dtype=np.float64).reshape(-1)
         p = theta.shape[0]
-        # a handle needs at least two particles: evaluate a 2-column ensemble and keep column 0
-        eng = Engine(p, n_obs, 2, d_panel_bytes=-1)       # forward maps only
-        try:
-            U = torch.from_numpy(np.stack([theta, theta], axis=1)).cuda()
-            G = torch.empty(n_obs, 2, dtype=torch.float64, device="cuda")
-            self.evaluate_ensemble(eng, U, G)
-            return G[:, 0].cpu().numpy()
-        finally:
-            eng.close()
+        # a handle needs at least two particles: evaluate a 2-column ensemble and keep column 0.  The forward-only handle
+        # and its two device buffers are kept on the model: a caller that loops over particles (ces/sample.py:121-196
+        # evaluates the model once per MCMC proposal) pays one small upload, one launch and one download per call, not a
+        # handle + cudaMalloc
+        key = (p, int(n_obs), torch.cuda.current_device())
+        cache = self.__dict__.get("_single_cache")
+        if cache is None or cache[0] != key:
+            if cache is not None:
+                cache[1].close()
+            cache = (key, Engine(p, n_obs, 2, d_panel_bytes=-1),       # forward maps only
+                     torch.empty(p, 2, dtype=torch.float64, device="cuda"),
+                     torch.empty(n_obs, 2, dtype=torch.float64, device="cuda"))
+            self.__dict__["_single_cache"] = cache
+        _, eng, U, G = cache
+        U.copy_(torch.from_numpy(np.stack([theta, theta], axis=1)))
+        self.evaluate_ensemble(eng, U, G)
+        return G[:, 0].cpu().numpy()
 
 
 class lineal(_DeviceMap):

@@ -193,6 +193,19 @@ int ces_host_update(ces_handle_t h, int ts_kind, double fixed_h, double* Uout_ho
  * block of U_next to host_out (dense, ld = cols_local; column chunks overlapped with the assembly).  One-shot; NULL cancels. */
 int ces_set_pending_output(ces_handle_t h, double* host_out);
 
+/* The whole loop of sampling.run (ces/calibrate.py:341-398) for a SMALL single-GPU problem (p <= 8, k <= 16, J <= 512,
+ * e.g. BASELINE config 1: d = 2, k = 10, J = 100, 1000 iterations) with one of the ces.utils maps as forward model, in ONE
+ * kernel launch: per iteration the forward map, the update, the cumulative pseudo-time and the stopping rule t > t_tol.
+ * U0_host: p x J.  xi_host: T x p x J pre-drawn N(0,1) noise (the caller's numpy stream), or NULL: device noise from
+ * (seed, step0 + iteration).  t0 / have_t0: time reached by earlier runs of the same sampler (resume).  Outputs (host):
+ * Utrace (n + 1) x p x J and Gtrace (n + 1) x k x J -- slot i is the ensemble before update i, slot n the final one --,
+ * S_host n x 16 step scalars (layout of ces_buffer "scalars"; the four diagnostics are sums over particles), t_host n
+ * cumulative times, *nsteps = n <= T updates performed.  A/b as in ces_forward_map (device), params_host its two scalars. */
+int ces_small_run(ces_handle_t h, int rule, int ts_kind, double fixed_h, double switch_, int map_kind, const double* A_dev,
+                  int64_t lda, const double* b_dev, const double* params_host, const double* U0_host, const double* xi_host,
+                  uint64_t seed, uint64_t step0, int64_t T, double t0, int have_t0, double t_tol, double* Utrace_host,
+                  double* Gtrace_host, double* S_host, double* t_host, int64_t* nsteps_host);
+
 /* Batched forward map G[:, j] = model(U[:, j]) for this rank's columns (enka.G_ens, ces/calibrate.py:106-130).
  * CES_MAP_LINEAL / _LOG: A_dev is k x p (ld = lda, even, 16-byte aligned), b_dev is k doubles or NULL.
  * CES_MAP_ELLIPTIC / _BANANA: params_host holds the two scalars named above, A_dev/b_dev are NULL. */
