@@ -516,6 +516,84 @@ class sampling(enka):
         return self._update_host('eki', y_obs, U0, Geval, Gamma, kwargs)
 
     # ------------------------------------------------------------------ the run loop
+    def _fused_small_run(self, eng, y_obs, U0, model, rule, kwargs, save_online, trace, device_map):
+        """The whole loop in ONE kernel launch (``ces_small_run``) when the problem fits a single CTA (p <= 8, k <= 16,
+        J <= 512 -- BASELINE config 1) and the forward model is one of the ``ces_b200.utils`` maps: forward, update,
+        cumulative time and the ``t_tol`` stopping rule run back to back on the device, the trace is the chain of
+        ensembles the kernel leaves in HBM, and the host downloads everything once.  Same results as the iteration-by-
+        iteration loop below (same arithmetic per step; the noise is the numpy stream the reference would consume: all T
+        draws are taken in one call and the generator is rewound to where an early stop leaves it).  Returns False when
+        the configuration needs the general loop."""
+        import ctypes
+
+        from . import _lib
+
+        kind = getattr(model, 'device_kind', None)
+        if not (device_map and eng.nranks == 1 and kind in _lib.MAPS and self.p <= 8 and self.n_obs <= 16
+                and 2 <= eng.J <= 512 and self.T >= 1 and self._step_options(rule, kwargs) == (None, None)
+                and kwargs.get('formulation', getattr(self, 'formulation', 'interaction')) == 'interaction'
+                and getattr(self, 'fused_run', True) and kwargs.get('xi', None) is None):
+            return False
+        p, k, J, T = self.p, self.n_obs, eng.J, int(self.T)
+        if (T + 1) * (2 * p + k) * J * 8 > (1 << 28):
+            return False
+        torch = eng.torch
+        A_dev, lda, b_dev, params = model._device_args(torch)
+        par = np.ascontiguousarray(params, dtype=np.float64) if params is not None else None
+        device_rng = kwargs.get('rng', getattr(self, 'rng', 'numpy')) == 'device'
+        xi_all, state = None, None
+        if rule != 'eki' and not device_rng:
+            state = np.random.get_state()
+            xi_all = np.random.normal(0, 1, [T, p, J])          # == T successive normal(0, 1, [p, J]) calls (:447,488,527)
+        t_hist = self.metrics['t']
+        Ut = np.empty((T + 1, p, J))
+        Gt = np.empty((T + 1, k, J))
+        S = np.empty((T, 16))
+        tv = np.empty(T)
+        n = ctypes.c_int64()
+        with eng.on_stream():
+            _lib.check(eng.lib.ces_small_run(
+                eng.h, _lib.RULES[rule], _lib.TS_FROBENIUS, 0.0, float(kwargs.get('switch', 1.)), _lib.MAPS[kind],
+                ctypes.c_void_p(A_dev.data_ptr()) if A_dev is not None else None, int(lda),
+                ctypes.c_void_p(b_dev.data_ptr()) if b_dev is not None else None,
+                _lib.host_ptr(par) if par is not None else None, _lib.host_ptr(U0),
+                _lib.host_ptr(xi_all) if xi_all is not None else None, int(kwargs.get('seed', getattr(self, 'seed', 0))),
+                len(t_hist), T, float(t_hist[-1]) if len(t_hist) else 0.0, 1 if len(t_hist) else 0,
+                float(kwargs.get('t_tol', 2.)), _lib.host_ptr(Ut), _lib.host_ptr(Gt), _lib.host_ptr(S), _lib.host_ptr(tv),
+                ctypes.byref(n)))
+        n = int(n.value)
+        if state is not None and n < T:
+            np.random.set_state(state)                           # an early stop consumed only n draws
+            np.random.normal(0, 1, [n, p, J])
+        self.update_rule = {'eks': 'eks_update', 'aldi': 'eks_update_linear', 'aldi_constant': 'eks_update_aldi',
+                            'eki': 'eki_update'}[rule]
+        # step scalars -> metrics (sums over particles / J), cumulative times
+        for name, col in (('self-bias', 1), ('bias', 2), ('self-bias-data', 3), ('bias-data', 4)):
+            self.metrics[name].extend((S[:n, col] / J).tolist())
+        self.metrics['t'].extend(tv[:n].tolist())
+        if save_online:
+            tag = model.model_name + '-eks-' + str(getattr(model, 'l_window', 0)).zfill(3) + '-' + str(self.J).zfill(4)
+            if hasattr(self, 'nexp'):
+                tag += '-' + str(self.nexp).zfill(2)
+            where = self.directory + '/ensembles/' + tag + '/'
+            try:
+                os.makedirs(where)
+            except OSError:
+                pass
+            for it in range(n):
+                np.save(where + 'ensemble_' + str(it).zfill(4), Ut[it])
+                np.save(where + 'Gensemble_' + str(it).zfill(4), Gt[it])
+            with open(where + 'metrics.pkl', "wb") as fh:
+                pickle.dump(self.metrics, fh)
+        if trace:
+            self.Uall = np.asarray(list(getattr(self, 'Uall', [])) + list(Ut[:n + 1]))
+            self.Gall = np.array(list(getattr(self, 'Gall', [])) + list(Gt[:n + 1]))
+        self.Ustar = Ut[n].copy()
+        self.Gstar = Gt[n].copy()
+        tail = '-' + str(self.J).zfill(4) + ('-' + str(self.nexp).zfill(2) if hasattr(self, 'nexp') else '') + '/'
+        self.online_path = self.directory + '/ensembles/' + model.model_name + tail
+        return True
+
     def run(self, y_obs, U0, model, Gamma, Jnoise, save_online=False, trace=True, **kwargs):
         """Ensemble Kalman sampler loop (ces/calibrate.py:270-416): forward -> trace -> update -> (save) ->
         stop when the cumulative pseudo-time exceeds ``t_tol`` (default 2.0) or after ``self.T`` iterations.
@@ -545,9 +623,12 @@ class sampling(enka):
             self.Uall = list(getattr(self, 'Uall', []))
             self.Gall = list(getattr(self, 'Gall', []))
         self._ensure_metrics()
+        known = rule in _RULE_METHOD
 
-        U_dev = torch.from_numpy(U0[:, lo:hi].copy()).to(dev)
         device_model = (not is_pde) and self._is_device_model(model)
+        if self._fused_small_run(eng, y_obs, U0, model, rule, kwargs, save_online, trace, known and device_model):
+            return
+        U_dev = torch.from_numpy(U0[:, lo:hi].copy()).to(dev)
         if is_pde:
             # initial conditions of the integrator, one per particle (ces/calibrate.py:317-327)
             t_ode, ws_pool = kwargs.get('t', None), kwargs.get('ws', None)
@@ -558,7 +639,6 @@ class sampling(enka):
             else:
                 self.W0 = np.tile(kwargs.get('wt', None), self.J).reshape(self.J, model.n_state).T
         G_dev = torch.empty(self.n_obs, hi - lo, dtype=torch.float64, device=dev)
-        known = rule in _RULE_METHOD
 
         device_pde = is_pde and getattr(model, 'device_kind', None) is not None and hasattr(model, 'evaluate_ensemble_pde')
         pde_state = {}

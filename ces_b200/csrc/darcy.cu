@@ -108,23 +108,26 @@ struct CoarseGeom {
     int H, HQ, HG, NCR, NCC, NA;
 };
 __host__ __device__ constexpr CoarseGeom coarse_geom(int K) {
-    const int H = ((K / 8 + 3) / 4) * 4;
+    // smallest aggregate side in {4, 8, 16} that leaves at most 8 x 8 aggregates; H/2 is a power of two (segmented shuffles)
+    const int H = K <= 32 ? 4 : (K <= 64 ? 8 : 16);
     return CoarseGeom{H, H / 2, H / 4, (K - 3) / H + 1, (K - 2) / H + 1, ((K - 3) / H + 1) * ((K - 2) / H + 1)};
 }
 constexpr int COARSE_SMEM_DOUBLES = 4096 + 64 + 64 + 128 + 320 + 256;
 // Threads per row of the 64 x 64 coarse solve, fixed by the default launch shape of each grid size (compile-time so the
 // short loops over a row unroll): 128 threads at K = 32, 288 at K = 48, 512 at K = 64 (256 with a 2-CTA cluster) and K = 128.
 __host__ __device__ constexpr int coarse_parts(int KH, bool cluster) {
-    return KH == 16 ? 2 : KH == 24 ? 4 : KH == 32 ? (cluster ? 4 : 8) : KH == 64 ? 8 : 0;
+    return KH == 16 ? 2 : KH == 24 ? 4 : KH == 32 ? (cluster ? 4 : 8) : KH == 64 ? 8 : (KH == 40 || KH == 48 || KH == 56) ? 4 : 0;
 }
 
 // One cluster of C CTAs per member; CTA `crank` owns the interior rows 1 + crank*4G ... (4G rows, G row groups of 4);
 // thread (g, q) owns rows 4g..4g+3 of the strip and the columns 2q, 2q+1.  blockDim.x = round_up(G * KH, 32), KH = K/2
 // is a template parameter so every shared-memory access is one base register plus an immediate offset.
+// The template grid K = 2 KH (a multiple of 16) may be larger than the member's grid: `Kact` x `Kact` nodes stored with row
+// pitch `ldk`; rows / columns from Kact - 1 on are padding (s = 0: inert, like boundary nodes), so any Nmesh <= 128 runs.
 template <int KH, bool CLUSTER, bool COARSE>
 __global__ void __launch_bounds__(TILE_THREADS, 1)
 darcy_pcg_tile_kernel(const double* __restrict__ cn, double* __restrict__ pn, int G, double tol2, int max_iter,
-                      int* __restrict__ iters_out) {
+                      int* __restrict__ iters_out, int Kact, int ldk) {
     constexpr int K = 2 * KH;
     cg::cluster_group cluster = cg::this_cluster();
     const int C = CLUSTER ? (int)cluster.num_blocks() : 1;        // CLUSTER == false: one CTA per member, no DSMEM traffic
@@ -156,7 +159,7 @@ darcy_pcg_tile_kernel(const double* __restrict__ cn, double* __restrict__ pn, in
     const int r0 = 1 + crank * R;
     const int i0 = r0 + 4 * g;
     const int lr = 4 * g + 1;           // local row of the tile's first row in the (R+2)-row planes
-    const double* cfield = cn + (size_t)member * K * K;
+    const double* cfield = cn + (size_t)member * Kact * ldk;
 
     for (int idx = tid; idx < 4 * plane + R * (KH + 1); idx += blockDim.x) pe[idx] = 0.0;      // pe, po, se, so, we
     for (int idx = tid; idx < 2 * K + (COARSE ? COARSE_SMEM_DOUBLES : 0); idx += blockDim.x) zh[idx] = 0.0;
@@ -176,11 +179,11 @@ darcy_pcg_tile_kernel(const double* __restrict__ cn, double* __restrict__ pn, in
         double cl[6][4], wl[4];
 #pragma unroll
         for (int a = 0; a < 6; ++a) {
-            const int row = min(max(i0 - 1 + a, 0), K - 1);
+            const int row = min(max(i0 - 1 + a, 0), Kact - 1);
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
-                const int col = min(max(2 * q - 1 + b, 0), K - 1);
-                cl[a][b] = active ? __ldg(cfield + (size_t)row * K + col) : 0.0;
+                const int col = min(max(2 * q - 1 + b, 0), Kact - 1);
+                cl[a][b] = active ? __ldg(cfield + (size_t)row * ldk + col) : 0.0;
             }
         }
 #pragma unroll
@@ -198,7 +201,7 @@ darcy_pcg_tile_kernel(const double* __restrict__ cn, double* __restrict__ pn, in
 #pragma unroll
             for (int b = 0; b < 2; ++b) {
                 const int row = i0 + a, col = 2 * q + b;
-                const bool ok = active && row <= K - 2 && col >= 1 && col <= K - 2;
+                const bool ok = active && row <= Kact - 2 && col >= 1 && col <= Kact - 2;
                 const double d = ((wv[a][b] + wv[a + 1][b]) + (b == 0 ? wl[a] : wi[a])) + (b == 0 ? wi[a] : wr[a]);
                 if (ok && d < 0.0) negmask |= 1u << (2 * a + b);
                 nvalid += ok ? 1 : 0;
@@ -250,7 +253,7 @@ darcy_pcg_tile_kernel(const double* __restrict__ cn, double* __restrict__ pn, in
     }
     // x = 0, r = b^ = s h^2, p = 0
     double x[4][2], r[4][2], p[4][2];
-    const double h2 = 1.0 / ((double)(K - 1) * (double)(K - 1));
+    const double h2 = 1.0 / ((double)(Kact - 1) * (double)(Kact - 1));
     double part = 0.0;
 #pragma unroll
     for (int a = 0; a < 4; ++a)
@@ -348,7 +351,7 @@ darcy_pcg_tile_kernel(const double* __restrict__ cn, double* __restrict__ pn, in
             auto at = [&](int i, int j) -> double& { return Ainv[(j % JP) * (64 * PARTS) + i * PARTS + j / JP]; };
             if (tid < 64) {
                 const int a = tid, ar = a / CG.NCC, ac = a - ar * CG.NCC;
-                if (a < CG.NA) {
+                if (a < CG.NA && cgath[a] != 0.0) {          // (an aggregate made of padding only has no entries)
                     at(a, a) = cgath[a];
                     if (ar > 0) at(a, a - CG.NCC) = cgath[64 + a];
                     if (ar < CG.NCR - 1) at(a, a + CG.NCC) = cgath[128 + a];
@@ -448,8 +451,9 @@ darcy_pcg_tile_kernel(const double* __restrict__ cn, double* __restrict__ pn, in
     };
     // boundary rows of the strip for the neighbour's copy of p: r plus the correction of the intermediate level (e1 = 0
     // without it), which the neighbour cannot know; it adds the coarse correction itself
+    const bool colok0 = 2 * q >= 1 && 2 * q <= Kact - 2, colok1 = 2 * q + 1 <= Kact - 2;    // interior columns of this thread
     auto push_rows = [&](double e1 = 0.0) {
-        const double e1a = q > 0 ? e1 : 0.0, e1b = q < KH - 1 ? e1 : 0.0;       // columns 0 and K-1 are boundary nodes
+        const double e1a = colok0 ? e1 : 0.0, e1b = colok1 ? e1 : 0.0;          // boundary / padding columns carry no correction
         if (first_group) st_async_f64x2(push_n_addr, r[0][0] + e1a, r[0][1] + e1b, push_n_bar);
         if (last_group) st_async_f64x2(push_s_addr, r[3][0] + e1a, r[3][1] + e1b, push_s_bar);
     };
@@ -588,13 +592,13 @@ darcy_pcg_tile_kernel(const double* __restrict__ cn, double* __restrict__ pn, in
                 }
                 if (first_group) {
                     const double2 z = *reinterpret_cast<const double2*>(zh + 2 * q);
-                    pe[q] = fma(beta, pe[q], CO ? z.x + (q > 0 ? ecn : 0.0) : z.x);
-                    po[q] = fma(beta, po[q], CO ? z.y + (q < KH - 1 ? ecn : 0.0) : z.y);
+                    pe[q] = fma(beta, pe[q], CO ? z.x + (colok0 ? ecn : 0.0) : z.x);
+                    po[q] = fma(beta, po[q], CO ? z.y + (colok1 ? ecn : 0.0) : z.y);
                 }
                 if (last_group) {
                     const double2 z = *reinterpret_cast<const double2*>(zh + K + 2 * q);
-                    pe_t[4 * KH] = fma(beta, pe_t[4 * KH], CO ? z.x + (q > 0 ? ecs : 0.0) : z.x);
-                    po_t[4 * KH] = fma(beta, po_t[4 * KH], CO ? z.y + (q < KH - 1 ? ecs : 0.0) : z.y);
+                    pe_t[4 * KH] = fma(beta, pe_t[4 * KH], CO ? z.x + (colok0 ? ecs : 0.0) : z.x);
+                    po_t[4 * KH] = fma(beta, po_t[4 * KH], CO ? z.y + (colok1 ? ecs : 0.0) : z.y);
                 }
             }
             __syncthreads();
@@ -676,9 +680,11 @@ darcy_pcg_tile_kernel(const double* __restrict__ cn, double* __restrict__ pn, in
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
             const int row = i0 + a;
-            if (row <= K - 2) {
-                double* out = pn + (size_t)member * K * K + (size_t)row * K + 2 * q;
-                *reinterpret_cast<double2*>(out) = make_double2(se[(lr + a) * KH + q] * x[a][0], so[(lr + a) * KH + q] * x[a][1]);
+            if (row <= Kact - 2 && 2 * q < Kact) {
+                double* out = pn + (size_t)member * Kact * ldk + (size_t)row * ldk + 2 * q;     // ldk is even: 16-byte aligned
+                const double v0 = se[(lr + a) * KH + q] * x[a][0], v1 = so[(lr + a) * KH + q] * x[a][1];
+                if (2 * q + 1 < Kact) *reinterpret_cast<double2*>(out) = make_double2(v0, v1);
+                else out[0] = v0;
             }
         }
     }
@@ -690,18 +696,22 @@ darcy_pcg_tile_kernel(const double* __restrict__ cn, double* __restrict__ pn, in
 }
 
 // G[o, col0 + m] = P[m, obs[o]]  (n_obs rows) -- or, with obs == nullptr, the full transposed field.
+// (fields are N x N with row pitch ldn, `cells` = N * ldn doubles per member; cell indices are row-major over N x N)
 __global__ void __launch_bounds__(256) darcy_gather_kernel(const double* __restrict__ P, long long cells, int members,
                                                            const long long* __restrict__ obs, int rows,
-                                                           double* __restrict__ G, long long ldg) {
+                                                           double* __restrict__ G, long long ldg, int N, int ldn) {
     const int m = blockIdx.x * 256 + threadIdx.x;
     const int o = blockIdx.y;
     if (m >= members) return;
     const long long cell = obs ? obs[o] : o;
-    G[(size_t)o * ldg + m] = P[(size_t)m * cells + cell];
+    const long long r = cell / N, c = cell - r * N;
+    G[(size_t)o * ldg + m] = P[(size_t)m * cells + r * ldn + c];
 }
 
 struct DarcyModel {
     int N = 0, p = 0, n_obs = 0;
+    int Kt = 0;                     // template grid of the solver: 2 * round_up(ceil(N / 2), 8) >= N
+    int ldn = 0;                    // row pitch of every N x N field: round_up(N, 2) (TMA operands need an even pitch)
     int tile_C = 1, tile_G = 0;     // solver: cluster size and row groups (of 4 rows) per CTA
     bool coarse = false;            // two-level preconditioner (aggregates aligned with tiles and strips)
     int64_t chunk = 0;
@@ -716,9 +726,9 @@ struct DarcyModel {
 };
 
 static int pcg_tile_launch(DarcyModel* m, const double* cn, double* pn, int members, double tol, int max_iter) {
-    const int K = m->N, KH = K / 2, R = 4 * m->tile_G;
+    const int K = m->Kt, KH = K / 2, R = 4 * m->tile_G;
     const size_t smem = ((size_t)4 * (R + 2) * KH + (size_t)R * (KH + 1) + 2 * K + (m->coarse ? COARSE_SMEM_DOUBLES : 0)) * sizeof(double);
-    typedef void (*TileKernel)(const double*, double*, int, double, int, int*);
+    typedef void (*TileKernel)(const double*, double*, int, double, int, int*, int, int);
 #define CES_TILE_ROW(CL, CO)                                                                                              \
     darcy_pcg_tile_kernel<8, CL, CO>, darcy_pcg_tile_kernel<16, CL, CO>, darcy_pcg_tile_kernel<24, CL, CO>,               \
         darcy_pcg_tile_kernel<32, CL, CO>, darcy_pcg_tile_kernel<40, CL, CO>, darcy_pcg_tile_kernel<48, CL, CO>,          \
@@ -746,7 +756,7 @@ static int pcg_tile_launch(DarcyModel* m, const double* cn, double* pn, int memb
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CES_CUDA(cudaLaunchKernelEx(&cfg, kernel, cn, pn, m->tile_G, tol * tol, max_iter, m->iters));
+    CES_CUDA(cudaLaunchKernelEx(&cfg, kernel, cn, pn, m->tile_G, tol * tol, max_iter, m->iters, m->N, m->ldn));
     CES_LAUNCHED(1);
     return CES_OK;
 }
@@ -761,46 +771,62 @@ int ces_darcy_create(int64_t N, int64_t p, const double* PhiT_host, const double
                      const int64_t* obs_host, int64_t n_obs, void* stream, void** out) {
     if (!out) return fail(CES_ERR_INVALID, "ces_darcy_create: null output%s", "");
     *out = nullptr;
-    if (N < 16 || N > 128 || N % 16 != 0 || p < 1 || p > N * N || !PhiT_host || !S_host || !S2_host || n_obs < 0 ||
-        (n_obs > 0 && !obs_host))
-        return fail(CES_ERR_INVALID, "ces_darcy_create: needs 16 <= N <= 128, N %% 16 == 0, 1 <= p <= N^2%s", "");
+    if (N < 4 || N > 128 || p < 1 || p > N * N || !PhiT_host || !S_host || !S2_host || n_obs < 0 || (n_obs > 0 && !obs_host))
+        return fail(CES_ERR_INVALID, "ces_darcy_create: needs 4 <= N <= 128 and 1 <= p <= N^2%s", "");
     for (int64_t o = 0; o < n_obs; ++o)
         if (obs_host[o] < 0 || obs_host[o] >= N * N) return fail(CES_ERR_INVALID, "ces_darcy_create: obs_index out of range%s", "");
     DarcyModel* m = new DarcyModel();
     m->N = (int)N; m->p = (int)p; m->n_obs = (int)n_obs;
+    m->ldn = (int)round_up(N, 2);
+    m->Kt = 2 * (int)round_up((N + 1) / 2, 8);             // the solver is instantiated for grids that are multiples of 16
     m->st = static_cast<cudaStream_t>(stream);
-    {   // NG row groups of 4 interior rows, G = ceil(NG / C) per CTA, G * N/2 threads <= TILE_THREADS
-        const int NG = (int)((N - 2 + 3) / 4), KH = (int)N / 2;
-        int tc = 1;
-        while (tc < 8 && ((NG + tc - 1) / tc) * KH > TILE_THREADS) tc *= 2;
-        if (const char* e = getenv("CES_DARCY_CLUSTER")) {          // experiments: a larger cluster than necessary
-            const int want = atoi(e);
-            if ((want == 1 || want == 2 || want == 4 || want == 8) && want >= tc && (want - 1) * ((NG + want - 1) / want) < NG)
-                tc = want;
-        }
-        m->tile_C = tc;
-        m->tile_G = (NG + tc - 1) / tc;
-        // two-level preconditioner: aggregates of H x H nodes need H/2 to be a power of two (segmented shuffles), strips
-        // that end on aggregate boundaries and at least 128 threads for the 64 x 64 coarse solve
-        const CoarseGeom cgm = coarse_geom((int)N);
+    {   // NG row groups of 4 interior rows over C CTAs, G per CTA, G * Kt/2 threads <= TILE_THREADS.  The coarse level
+        // needs strips that end on aggregate boundaries (G a multiple of H/4 in a cluster) and >= 64 * parts threads for
+        // the 64 x 64 coarse solve: the smallest cluster that can have it is taken, else the smallest cluster at all.
+        const int NG = (int)((N - 2 + 3) / 4), KH = m->Kt / 2;
+        const CoarseGeom cgm = coarse_geom(m->Kt);
         const bool pow2 = (cgm.HQ & (cgm.HQ - 1)) == 0;
-        const int threads = (int)round_up((int64_t)m->tile_G * KH, 32);
-        const int parts = coarse_parts(KH, tc > 1);
-        m->coarse = pow2 && parts >= 2 && threads >= 64 * parts && (tc == 1 || (4 * m->tile_G) % cgm.H == 0);
-        if (const char* e = getenv("CES_DARCY_COARSE")) m->coarse = m->coarse && atoi(e) != 0;      // experiments: 0 disables
+        bool want_coarse = true;
+        if (const char* e = getenv("CES_DARCY_COARSE")) want_coarse = atoi(e) != 0;      // experiments: 0 disables
+        int forced = 0;
+        if (const char* e = getenv("CES_DARCY_CLUSTER")) forced = atoi(e);              // experiments: a given cluster size
+        int tc_plain = 0, g_plain = 0;
+        m->tile_C = 0;
+        for (int tc = 1; tc <= 8 && m->tile_C == 0; ++tc) {
+            if (forced >= 1 && forced <= 8 && tc != forced) continue;
+            const int g0 = (NG + tc - 1) / tc;
+            if (g0 * KH > TILE_THREADS) continue;
+            if (!tc_plain) { tc_plain = tc; g_plain = g0; }
+            const int parts = coarse_parts(KH, tc > 1);
+            const int gc = tc > 1 ? (int)round_up(g0, cgm.HG) : g0;
+            const int threads = (int)round_up((int64_t)gc * KH, 32);
+            if (want_coarse && pow2 && parts >= 2 && gc * KH <= TILE_THREADS && threads >= 64 * parts) {
+                m->tile_G = gc;
+                m->tile_C = (NG + gc - 1) / gc;            // rounding G up may leave the last CTA without rows: drop it
+                m->coarse = true;
+            }
+        }
+        if (m->tile_C == 0) {
+            if (!tc_plain) { delete m; return fail(CES_ERR_INVALID, "ces_darcy_create: no launch shape for this grid%s", ""); }
+            m->tile_C = tc_plain; m->tile_G = g_plain; m->coarse = false;
+        }
     }
-    const int64_t cells = N * N;
+    const int64_t cells = N * m->ldn;              // doubles per stored field (row pitch ldn)
     m->chunk = (1ll << 29) / (cells * 8);          // 512 MiB per field buffer
     if (m->chunk > 32768) m->chunk = 32768;
     if (m->chunk < 64) m->chunk = 64;
-    auto up = [&](double** dst, const double* src, int64_t n) -> int {
-        CES_CUDA(cudaMalloc(dst, n * sizeof(double)));
-        CES_CUDA(cudaMemcpyAsync(*dst, src, n * sizeof(double), cudaMemcpyHostToDevice, m->st));
+    // constant operators, re-packed to the even row pitch (zero padding): Phi^T p x (N x ldn), S and S2 N x ldn
+    auto up2d = [&](double** dst, const double* src, int64_t rows, int64_t width, int64_t pitch) -> int {
+        CES_CUDA(cudaMalloc(dst, rows * pitch * sizeof(double)));
+        CES_CUDA(cudaMemsetAsync(*dst, 0, rows * pitch * sizeof(double), m->st));
+        CES_CUDA(cudaMemcpy2DAsync(*dst, pitch * sizeof(double), src, width * sizeof(double), width * sizeof(double), rows,
+                                   cudaMemcpyHostToDevice, m->st));
         return CES_OK;
     };
-    int s = up(&m->PhiT, PhiT_host, p * cells);
-    if (s == CES_OK) s = up(&m->S, S_host, N * N);
-    if (s == CES_OK) s = up(&m->S2, S2_host, N * N);
+    int s = up2d(&m->PhiT, PhiT_host, p * N, N, m->ldn);
+    if (s == CES_OK) s = up2d(&m->S, S_host, N, N, m->ldn);
+    if (s == CES_OK) s = up2d(&m->S2, S2_host, N, N, m->ldn);
+
     if (s == CES_OK && n_obs > 0) {
         if (cudaMalloc(&m->obs, n_obs * sizeof(long long)) != cudaSuccess) s = fail(CES_ERR_NOMEM, "cudaMalloc failed%s", "");
         else if (cudaMemcpyAsync(m->obs, obs_host, n_obs * sizeof(long long), cudaMemcpyHostToDevice, m->st) != cudaSuccess)
@@ -831,8 +857,8 @@ int ces_darcy_forward(void* handle, const double* U, int64_t ldu, int64_t cols, 
     if (!m || !U || !G || cols < 0 || ldu < cols || ldg < cols) return fail(CES_ERR_INVALID, "ces_darcy_forward: bad argument%s", "");
     if (!full_solution && m->n_obs == 0) return fail(CES_ERR_STATE, "ces_darcy_forward: no obs_index was given%s", "");
     if (cols == 0) return CES_OK;
-    const int N = m->N, p = m->p;
-    const int64_t cells = (int64_t)N * N;
+    const int N = m->N, p = m->p, ldn = m->ldn;
+    const int64_t cells = (int64_t)N * ldn;        // doubles per stored field
     cudaStream_t st = m->st;
     if (tol <= 0.0) tol = 1e-13;
     if (max_iter <= 0) max_iter = 40 * N;
@@ -877,12 +903,12 @@ int ces_darcy_forward(void* handle, const double* U, int64_t ldu, int64_t cols, 
         GemmCall t1;
         t1.a_mode = A_MK; t1.b_mode = B_NK;
         t1.M = (int)(mc * N); t1.N = N; t1.K = N;
-        t1.A = m->B0; t1.lda = N; t1.B = m->S; t1.ldb = N; t1.C = m->B1; t1.ldc = N;
+        t1.A = m->B0; t1.lda = ldn; t1.B = m->S; t1.ldb = ldn; t1.C = m->B1; t1.ldc = ldn;
         CES_TRY(gemm(st, t1));
         GemmCall cz;
         cz.a_mode = A_MK; cz.b_mode = B_KN;
         cz.M = N; cz.N = N; cz.K = N;
-        cz.A = m->S; cz.lda = N; cz.B = m->B1; cz.ldb = N; cz.C = m->B2; cz.ldc = N;
+        cz.A = m->S; cz.lda = ldn; cz.B = m->B1; cz.ldb = ldn; cz.C = m->B2; cz.ldc = ldn;
         cz.batch = mc; cz.b_batch_rows = N; cz.c_batch_elems = cells;
         CES_TRY(gemm(st, cz));
         // 4. solve; nodal pressure into B0 (cleared: boundary nodes stay zero)
@@ -904,9 +930,9 @@ int ces_darcy_forward(void* handle, const double* U, int64_t ldu, int64_t cols, 
         pz.A = m->S2; pz.B = m->B1; pz.C = m->B2;
         CES_TRY(gemm(st, pz));
         // 6. observations (or the whole field), particle index contiguous
-        const int rows = full_solution ? (int)cells : m->n_obs;
+        const int rows = full_solution ? N * N : m->n_obs;
         dim3 grid((unsigned)ceil_div(mc, 256), (unsigned)rows);
-        darcy_gather_kernel<<<grid, 256, 0, st>>>(m->B2, cells, (int)mc, full_solution ? nullptr : m->obs, rows, G + c0, ldg);
+        darcy_gather_kernel<<<grid, 256, 0, st>>>(m->B2, cells, (int)mc, full_solution ? nullptr : m->obs, rows, G + c0, ldg, N, ldn);
         CES_LAUNCHED(1);
     }
     int iters = 0;

@@ -25,6 +25,50 @@ struct SmallArgs {
     double* S;                           // device scalars (StepScalars layout; S_INFO reports a failed pivot)
 };
 
+// Column j of V = U~ D with D = (1/J) E^T W never stored, and this column's share of ||D||_F^2: the one loop of the step
+// that is O(J) per thread.  K and P are compile-time trip counts (the generic, predicated form of this loop spent 87 % of
+// the kernel on branches and address arithmetic -- 166 instructions per particle pair for 13 useful DFMAs); four
+// independent particles i are in flight per trip, so the FMA chains of d overlap.
+template <int KK, int PP>
+__device__ __forceinline__ void interaction_column(const double* __restrict__ Es, const double* __restrict__ Uts, int J, int p,
+                                                   const double (&w)[SMALL_K_MAX], double invJ, double (&v)[SMALL_P_MAX],
+                                                   double& ssq) {
+    double s0 = 0.0, s1 = 0.0;
+    int i = 0;
+    for (; i + 1 < J; i += 2) {
+        double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+        for (int m = 0; m < KK; ++m) {
+            d0 = fma(Es[m * J + i], w[m], d0);
+            d1 = fma(Es[m * J + i + 1], w[m], d1);
+        }
+        d0 *= invJ; d1 *= invJ;
+        s0 = fma(d0, d0, s0); s1 = fma(d1, d1, s1);
+#pragma unroll
+        for (int q = 0; q < PP; ++q)
+            if (q < p) v[q] = fma(Uts[q * J + i + 1], d1, fma(Uts[q * J + i], d0, v[q]));
+    }
+    if (i < J) {
+        double d0 = 0.0;
+#pragma unroll
+        for (int m = 0; m < KK; ++m) d0 = fma(Es[m * J + i], w[m], d0);
+        d0 *= invJ;
+        s0 = fma(d0, d0, s0);
+#pragma unroll
+        for (int q = 0; q < PP; ++q)
+            if (q < p) v[q] = fma(Uts[q * J + i], d0, v[q]);
+    }
+    ssq += s0 + s1;
+}
+
+template <int KK>
+__device__ __forceinline__ void interaction_column_p(const double* Es, const double* Uts, int J, int p, const double (&w)[SMALL_K_MAX],
+                                                     double invJ, double (&v)[SMALL_P_MAX], double& ssq) {
+    if (p <= 2) interaction_column<KK, 2>(Es, Uts, J, p, w, invJ, v, ssq);
+    else if (p <= 4) interaction_column<KK, 4>(Es, Uts, J, p, w, invJ, v, ssq);
+    else interaction_column<KK, 8>(Es, Uts, J, p, w, invJ, v, ssq);
+}
+
 __device__ __forceinline__ void block_reduce5(double (&v)[5], double (*scratch)[32], bool take_max4) {
     // sums of v[0..3] (+ v[4]: sum, or max when take_max4); every thread returns the totals
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
@@ -142,14 +186,12 @@ __device__ __forceinline__ void small_step_body(const SmallArgs& a, double* sm, 
     for (int q = 0; q < SP; ++q) v[q] = 0.0;
     if (on) {
         const double invJ = 1.0 / (double)J;
-        for (int i = 0; i < J; ++i) {
-            double d = 0.0;
-#pragma unroll
-            for (int m = 0; m < SK; ++m) if (m < k) d += Es[(size_t)m * J + i] * w[m];
-            d *= invJ;
-            red[0] += d * d;
-#pragma unroll
-            for (int q = 0; q < SP; ++q) if (q < p) v[q] += Uts[(size_t)q * J + i] * d;
+        switch (k) {
+#define CES_IC(KK) case KK: interaction_column_p<KK>(Es, Uts, J, p, w, invJ, v, red[0]); break;
+            CES_IC(1) CES_IC(2) CES_IC(3) CES_IC(4) CES_IC(5) CES_IC(6) CES_IC(7) CES_IC(8)
+            CES_IC(9) CES_IC(10) CES_IC(11) CES_IC(12) CES_IC(13) CES_IC(14) CES_IC(15) CES_IC(16)
+#undef CES_IC
+            default: break;
         }
     }
     // ---- C^uu = U~ U~^T / (J-1) (+1e-8 I); 1/J for the semi-implicit rule (:424, :476, :512)

@@ -161,8 +161,9 @@ class model(object):
         if not torch.cuda.is_available():
             raise RuntimeError("ces_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         N = int(self.Nmesh)
-        if N % 16 != 0 or N < 16:
-            raise NotImplementedError("the device Darcy path needs Nmesh to be a multiple of 16 (got %d)" % N)
+        if not 4 <= N <= 128:
+            raise NotImplementedError("the device Darcy path covers 4 <= Nmesh <= 128 (got %d): one member must fit the "
+                                      "registers and shared memory of one thread-block cluster" % N)
         phiT = np.ascontiguousarray(kl_operator(N, self.alpha, self.tau, self._modes()))
         centres = (np.arange(N) + 0.5) / N
         nodes = np.arange(N) / (N - 1.0)

@@ -8,8 +8,8 @@ preconditioner
 
     M^-1 = I + P1 diag(P1^T A^ P1)^-1 P1^T + Pc (Pc^T A^ Pc)^-1 Pc^T ,
 
-P1 = piecewise constants on aggregates of 4 x 4 nodes, Pc = on aggregates of H x H nodes (H = 16 at Nmesh = 128, 8 at
-64, 4 at 32; rows grouped from the first interior row, columns from the boundary column, exactly like the device's
+P1 = piecewise constants on aggregates of 4 x 4 nodes, Pc = on aggregates of H x H nodes (H = 16 for Nmesh > 64, 8 for
+Nmesh > 32, else 4; rows grouped from the first interior row, columns from the boundary column, exactly like the device's
 thread tiles), stopping when r.M^-1 r <= tol^2 r0.M^-1 r0.  This file restates that algorithm so that the tests can (a)
 check it against the direct solve of oracle/darcy_oracle.py on the CPU and (b) hold the device kernel to its iteration
 counts: the preconditioner is part of the product's arithmetic and deserves an oracle of its own.
@@ -41,8 +41,15 @@ def system(theta):
 
 
 def coarse_size(K):
-    """Aggregate side of the coarse level (ces_b200/csrc/darcy.cu: coarse_geom)."""
-    return ((K // 8 + 3) // 4) * 4
+    """Aggregate side of the coarse level (ces_b200/csrc/darcy.cu: coarse_geom on the template grid, the next multiple
+    of 16 >= K): the smallest of 4, 8, 16 that leaves at most 8 x 8 aggregates."""
+    Kt = 2 * (((K + 1) // 2 + 7) // 8 * 8)
+    return 4 if Kt <= 32 else (8 if Kt <= 64 else 16)
+
+
+def has_coarse_level(K):
+    """Grids of at most 16 nodes a side run plain Jacobi scaling on the device (too few threads for the coarse solve)."""
+    return 2 * (((K + 1) // 2 + 7) // 8 * 8) > 16
 
 
 def aggregates(K, hr, hc):
@@ -63,6 +70,8 @@ def solve(theta, tol=1e-13, max_iter=None, levels=("pair", "coarse")):
     Ah = (sp.diags(s) @ A @ sp.diags(s)).tocsr()
     b = s / float(K - 1) ** 2
     terms = []
+    if not has_coarse_level(K) or A.diagonal().min() < 0.0:     # (a member with a negative diagonal runs plain scaling too)
+        levels = ()
     if "pair" in levels and coarse_size(K) > 4:      # at Nmesh = 32 the coarse aggregates are these very blocks
         P1 = aggregates(K, 4, 4)
         terms.append((P1, 1.0 / np.asarray((P1.T @ Ah @ P1).diagonal()).ravel(), None))

@@ -137,3 +137,45 @@ def test_ill_conditioned_dense_gamma_is_as_accurate_as_the_reference_solve(cond)
     assert err_ours <= max(10.0 * err_ref, 1e-10), (cond, err_ours, err_ref)
     if cond <= 1e2:
         assert err_ours < 1e-10
+
+
+@pytest.mark.parametrize("kind,rule", [("lineal", "aldi"), ("lineal", "eks"), ("lineal", "aldi_constant"), ("lineal", "eki"),
+                                       ("lineal_log", "aldi"), ("elliptic", "aldi"), ("banana", "eks")])
+def test_fused_small_run_equals_the_iteration_by_iteration_loop(kind, rule):
+    """ces_small_run (the whole run loop of a small problem in one launch) against the general loop of the same class:
+    trace, forward outputs, metrics, stopping iteration and the state the global numpy generator is left in."""
+    rs = np.random.RandomState(4)
+    if kind in ("lineal", "lineal_log"):
+        d, k, J = 2, 10, 100
+        A = rs.normal(size=(k, d)) * (0.3 if kind == "lineal_log" else 1.0)
+        model = cutils.lineal(A, b=0.25) if kind == "lineal" else cutils.lineal_log(A)
+        ustar = np.array([[-1.0], [0.5]])
+        y = model(ustar[:, 0]) + 0.05 * rs.normal(size=k)
+        Gamma = 0.01 * np.eye(k) + (0.002 * np.ones((k, k)) if rule == "eks" else 0.0)      # dense Gamma for one rule
+    else:
+        d, k, J = 2, 2, 64
+        model = cutils.elliptic() if kind == "elliptic" else cutils.banana()
+        ustar = np.array([[-2.65], [104.5]]) if kind == "elliptic" else np.array([[0.5], [1.0]])
+        y = np.asarray(model(ustar[:, 0]), dtype=float)
+        Gamma = 0.01 * np.eye(2)
+    U0 = ustar + rs.normal(size=(d, J))
+    out = {}
+    for fused in (True, False):
+        s = calibrate.sampling(d, k, J)
+        s.ustar, s.mu, s.sigma, s.T, s.fused_run = ustar, np.zeros((d, 1)) + ustar, 25.0 * np.eye(d), 25, fused
+        np.random.seed(9)
+        s.run(y, U0, model, Gamma, None, update=rule, t_tol=0.05)
+        out[fused] = (s, np.random.get_state()[1].copy(), np.random.get_state()[2:])
+    (a, sa, ta), (b, sb, tb) = out[True], out[False]
+    n = len(b.metrics["t"])
+    assert len(a.metrics["t"]) == n and 1 <= n <= 25 and a.Uall.shape == b.Uall.shape == (n + 1, d, J)
+    scale = np.abs(b.Uall).max()
+    assert np.abs(a.Uall - b.Uall).max() / scale < 1e-9 and np.abs(a.Gall - b.Gall).max() / max(np.abs(b.Gall).max(), 1e-300) < 1e-9
+    for key in ("self-bias", "bias", "self-bias-data", "bias-data", "t"):
+        assert np.allclose(a.metrics[key], b.metrics[key], rtol=1e-8, atol=0), key
+    assert np.array_equal(a.Ustar, a.Uall[-1]) and np.array_equal(a.Gstar, a.Gall[-1]) and a.update_rule == b.update_rule
+    assert np.array_equal(sa, sb) and ta == tb                      # the generator is where the reference would leave it
+    # resume through the fused path: the time keeps accumulating, the trace grows
+    a.T = 3
+    a.run(y, a.Ustar, model, Gamma, None, update=rule, t_tol=1e9)
+    assert a.Uall.shape[0] == n + 1 + 4 and len(a.metrics["t"]) == n + 3 and np.all(np.diff(a.metrics["t"]) > 0)

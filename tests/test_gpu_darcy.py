@@ -17,7 +17,10 @@ def _rel(a, b):
 
 @pytest.mark.parametrize("N,p,members,scale", [(16, 10, 7, 1.0), (16, 10, 5, 10.0), (32, 24, 4, 3.0), (64, 64, 4, 1.0),
                                                (64, 64, 3, 10.0), (128, 256, 2, 1.0), (48, 30, 3, 2.0), (80, 40, 2, 1.0),
-                                               (96, 64, 2, 1.0), (112, 64, 2, 3.0)])
+                                               (96, 64, 2, 1.0), (112, 64, 2, 3.0),
+                                               # any Nmesh (ces/darcy.py:10), not only multiples of 16: even, odd, tiny
+                                               (50, 30, 3, 1.0), (100, 64, 2, 2.0), (33, 20, 3, 1.0), (77, 40, 2, 1.0),
+                                               (127, 64, 2, 1.0), (8, 6, 4, 1.0), (21, 12, 3, 3.0)])
 def test_truncated_model_matches_oracle(N, p, members, scale):
     rng = np.random.default_rng(N + p)
     U = scale * rng.standard_normal((p, members))
@@ -140,7 +143,8 @@ def test_solver_statistics_and_coarse_level(monkeypatch):
     assert _rel(full, jac) < 1e-10
 
 
-@pytest.mark.parametrize("N,p,scale", [(32, 24, 1.0), (48, 30, 1.0), (64, 64, 1.0), (64, 64, 10.0), (128, 256, 1.0)])
+@pytest.mark.parametrize("N,p,scale", [(32, 24, 1.0), (48, 30, 1.0), (64, 64, 1.0), (64, 64, 10.0), (128, 256, 1.0),
+                                       (80, 40, 1.0), (96, 64, 1.0), (112, 64, 1.0), (100, 64, 1.0), (77, 40, 1.0)])
 def test_iteration_counts_match_the_pcg_oracle(N, p, scale):
     """The kernel runs the algorithm oracle/darcy_pcg_oracle.py restates (scaled CG, 4 x 4 level, aggregation coarse
     level, same stopping rule): besides the solution, its iteration counts must be the oracle's, member by member in sum
@@ -156,3 +160,20 @@ def test_iteration_counts_match_the_pcg_oracle(N, p, scale):
     _, total, _ = m.last_stats()
     want = sum(dp.solve(ref.eval_rf(U[:, j]))[1] for j in range(members))
     assert abs(total - want) <= max(3, 0.02 * want), (total, want)
+
+
+def test_poisson_limit_matches_the_series_solution():
+    """theta = 0 (all KL coefficients zero) => -Laplace(p) = 1 with zero boundary values: the device solution against the
+    double sine series at the cell centres, second order in h (tests/test_darcy_analytic.py holds the oracle to the same
+    closed form) -- a check of the discretisation that does not go through the scipy restatement."""
+    from test_darcy_analytic import poisson_series
+
+    errs = []
+    for N in (16, 32, 64, 128):
+        m = cdarcy.model_trunc(Nmesh=N, p=6)
+        p = m.solve_ensemble(np.zeros((6, 2)), full_solution=True)[:, 0].reshape(N, N)
+        centres = (np.arange(N) + 0.5) / N
+        errs.append(np.abs(p - poisson_series(centres, centres)).max())
+        assert errs[-1] < 0.6 / (N - 1) ** 2
+    assert all(3.0 < errs[i] / errs[i + 1] < 5.5 for i in range(3))
+    assert abs(p.max() - 0.0736713) < 2e-5
