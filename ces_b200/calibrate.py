@@ -79,6 +79,14 @@ def _identity(a):
     return (id(a), a.__array_interface__['data'][0], a.shape, a.strides, a.dtype.str)
 
 
+def _consume_model_rng(model, n_particles):
+    """Advance numpy's global generator by what the reference's per-particle loop over ``model`` would have drawn
+    (``rng_draws_per_call`` normals per evaluation; only ``banana`` has any, ces/utils.py:122)."""
+    draws = int(getattr(model, 'rng_draws_per_call', 0))
+    if draws and n_particles:
+        np.random.normal(0, 1, [int(n_particles), draws])
+
+
 class _HostTrace(object):
     """Device -> host copies of the per-iteration ensembles that do not stall the loop (``trace`` / ``save_online`` of
     ``sampling.run``).  ``push`` queues an asynchronous copy into fresh page-locked memory on a side
@@ -193,6 +201,7 @@ class enka(object):
             U = torch.from_numpy(padded).cuda()
             G = torch.empty(self.n_obs, width, dtype=torch.float64, device="cuda")
             model.evaluate_ensemble(cache[1], U, G)
+            _consume_model_rng(model, n)
             return G[:, :n].cpu().numpy()
         return self._host_G_ens(theta, model)
 
@@ -542,9 +551,16 @@ class sampling(enka):
         par = np.ascontiguousarray(params, dtype=np.float64) if params is not None else None
         device_rng = kwargs.get('rng', getattr(self, 'rng', 'numpy')) == 'device'
         xi_all, state = None, None
-        if rule != 'eki' and not device_rng:
+        fdraws = int(getattr(model, 'rng_draws_per_call', 0)) * J    # normals the reference's forward loop draws per pass
+        host_noise = rule != 'eki' and not device_rng
+        if host_noise or fdraws:
+            # per iteration the reference draws [forward pass: fdraws][update: p * J] (:351-352 then :447,488,527), and
+            # fdraws once more for the final forward pass; all T iterations are drawn in one call (the same stream)
             state = np.random.get_state()
-            xi_all = np.random.normal(0, 1, [T, p, J])          # == T successive normal(0, 1, [p, J]) calls (:447,488,527)
+            per = fdraws + (p * J if host_noise else 0)
+            raw = np.random.normal(0, 1, [T, per])
+            if host_noise:
+                xi_all = np.ascontiguousarray(raw[:, fdraws:]).reshape(T, p, J)
         t_hist = self.metrics['t']
         Ut = np.empty((T + 1, p, J))
         Gt = np.empty((T + 1, k, J))
@@ -562,9 +578,12 @@ class sampling(enka):
                 float(kwargs.get('t_tol', 2.)), _lib.host_ptr(Ut), _lib.host_ptr(Gt), _lib.host_ptr(S), _lib.host_ptr(tv),
                 ctypes.byref(n)))
         n = int(n.value)
-        if state is not None and n < T:
-            np.random.set_state(state)                           # an early stop consumed only n draws
-            np.random.normal(0, 1, [n, p, J])
+        if state is not None:
+            if n < T:
+                np.random.set_state(state)                       # an early stop consumed only n iterations' draws
+                np.random.normal(0, 1, [n, fdraws + (p * J if host_noise else 0)])
+            if fdraws:
+                np.random.normal(0, 1, fdraws)                   # the final forward pass
         self.update_rule = {'eks': 'eks_update', 'aldi': 'eks_update_linear', 'aldi_constant': 'eks_update_aldi',
                             'eki': 'eki_update'}[rule]
         # step scalars -> metrics (sums over particles / J), cumulative times
@@ -693,6 +712,7 @@ class sampling(enka):
                 return forward_pde(U_dev, final)
             if device_model:
                 model.evaluate_ensemble(eng, U_dev, G_dev)
+                _consume_model_rng(model, J)                # (every rank: the stream is global)
                 return G_dev, None
             G_host = self._host_G_ens(U_dev.cpu().numpy(), model)
             G_dev.copy_(torch.from_numpy(np.ascontiguousarray(G_host[:self.n_obs])))

@@ -152,8 +152,14 @@ class elliptic(_DeviceMap):
 
 
 class banana(_DeviceMap):
-    """(a u1, u2/a - b (u1^2 + a^2)).  ces/utils.py:91-122."""
+    """(a u1, u2/a - b (u1^2 + a^2)).  ces/utils.py:91-122.
+
+    The reference draws ``np.random.normal(0, 1, [2])`` in EVERY evaluation -- ``flag_noise * chol(Gamma).dot(normal)``
+    (:122) multiplies the draw by zero instead of skipping it -- so a seeded script's random stream advances by two
+    normals per particle per forward pass.  ``rng_draws_per_call`` tells the batched callers (``sampling.run``,
+    ``enka.G_ens``, ``MCMC.model_mh``) to consume the same variates, so the noise that follows is the reference's."""
     device_kind = "banana"
+    rng_draws_per_call = 2
 
     def __init__(self, a=1.0, b=.5, rho=.9, flag_noise=False):
         self.flag_noise = flag_noise
@@ -175,8 +181,9 @@ class banana(_DeviceMap):
 
     def __call__(self, theta, dG=False):
         out = self._single(theta, 2)
+        z = np.random.normal(0, 1, [2, ])                   # drawn unconditionally, like the reference (:122)
         if self.flag_noise:
-            out = out + np.linalg.cholesky(self.Gamma).dot(np.random.normal(0, 1, [2, ]))
+            out = out + np.linalg.cholesky(self.Gamma).dot(z)
         return out
 
 

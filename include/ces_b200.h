@@ -288,6 +288,24 @@ int ces_potrf(void* stream, double* A_dev, int64_t ld, int64_t n);
 /* X = A^-1 B for SPD A (n x n) and B (n x nrhs), both on the device; A is overwritten by its factor. */
 int ces_posv(void* stream, double* A_dev, int64_t lda, int64_t n, double* B_dev, int64_t ldb, int64_t nrhs);
 
+/* ---- Metropolis-Hastings on the true forward model: MCMC.model_mh (ces/sample.py:121-196) ---------------------------
+ * n_chains independent chains of n_mcmc proposals, one warp per chain, the loop entirely on the device (csrc/mcmc.cu).
+ * Forward model: one of the ces.utils maps (A_dev / b_dev / params_host as in ces_forward_map).  Host inputs:
+ * y (k), Ginv2 = (2 Gamma)^-1 (k x k, dense), prior mean mu (p) and precision Pinv (p x p) -- unused with pcn != 0 --,
+ * scales (p x p: delta * chol(cov(Ustar)), or chol(prior.cov) for pCN), beta (pCN), start (n_chains x p: first state of
+ * every chain) and phi_point (n_chains x p: where the initial Phi_current is evaluated; the reference uses the ensemble
+ * mean even when it resumes from its last sample).  Random numbers: with mt_state_host != NULL chain 0 consumes numpy's
+ * global MT19937 stream exactly as np.random.normal(0, 1, p) followed by np.random.uniform() would -- mt_state_host =
+ * 624 key words, position, has_gauss flag (626 uint32), *mt_gauss_host = the cached Gaussian; both are updated to the
+ * state after the run --; every other chain (all of them with NULL) draws from Philox keyed by (seed, chain, iteration).
+ * Outputs: samples (n_chains x (n_mcmc + 1) x p, state 0 = start) and the number of accepted proposals per chain. */
+int ces_mcmc_model_mh(void* stream, int map_kind, int64_t p, int64_t k, const double* A_dev, int64_t lda,
+                      const double* b_dev, const double* params_host, const double* y_host, const double* Ginv2_host,
+                      const double* mu_host, const double* Pinv_host, const double* scales_host, int pcn, double beta,
+                      int64_t n_mcmc, int64_t n_chains, const double* start_host, const double* phi_point_host,
+                      uint32_t* mt_state_host, double* mt_gauss_host, uint64_t seed, double* samples_host,
+                      int32_t* accepted_host);
+
 #ifdef __cplusplus
 }
 #endif

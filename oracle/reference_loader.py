@@ -63,6 +63,27 @@ def load_utils():
     return mod
 
 
+def load_sample():
+    """The reference ``ces/sample.py`` (class ``MCMC``).  Its module-level ``import gpflow`` and the package-relative
+    imports of ``calibrate`` / ``emulate`` cannot be satisfied here (GPflow is absent, calibrate has the TabError), so the
+    file is exec'd, unmodified, into a private module with stand-ins for those three names: ``model_mh`` -- the only
+    method used -- touches none of them.  Needs ``ces/sample.py`` under REFERENCE_ROOT (not staged for the GPU box: the
+    GPU tests use golden vectors made here)."""
+    if "sample" in _cache:
+        return _cache["sample"]
+    path = os.path.join(REFERENCE_ROOT, "ces", "sample.py")
+    with open(path) as fh:
+        src = fh.read().expandtabs(4)
+    src = src.replace("from . import calibrate", "calibrate = None").replace("from . import emulate", "emulate = None")
+    src = src.replace("import gpflow as gp", "gp = None")
+    src = src.replace("from tqdm.autonotebook import tqdm", "from tqdm import tqdm")
+    mod = types.ModuleType("ces_sample_reference")
+    mod.__file__ = path
+    exec(compile(src, path, "exec"), mod.__dict__)
+    _cache["sample"] = mod
+    return mod
+
+
 def make_sampler(p, n_obs, J, mu, sigma, ustar, T=30, t_hist=None):
     """A reference ``sampling`` object primed so one update rule can be called
     directly, outside ``run`` (which is what creates these attributes,

@@ -40,6 +40,17 @@ def main():
     out.update(first_Uall=first["Uall"], first_t=np.array(first["t"]), Uall=np.array(eks.Uall), Gall=np.array(eks.Gall),
                Ustar=eks.Ustar, Gstar=eks.Gstar,
                metrics=np.array([eks.metrics[key] for key in ("self-bias", "bias", "self-bias-data", "bias-data", "t")]))
+    # banana: the reference's model draws two normals per evaluation even without noise (ces/utils.py:122), so the update
+    # noise of a seeded run is interleaved with them; a drop-in must consume the same stream
+    ban = utils.banana()
+    rs = np.random.RandomState(2)
+    Ub = np.array([[0.4], [1.0]]) + 0.5 * rs.normal(size=(2, 30))
+    eb = cal.sampling(p=2, n_obs=2, J=30)
+    eb.ustar, eb.mu, eb.sigma, eb.T = np.array([[0.4], [1.0]]), np.zeros((2, 1)), 9.0 * np.eye(2), 4
+    np.random.seed(8)
+    eb.run(np.array([0.4, 0.3]), Ub, ban, ban.Gamma, None, t_tol=1e9)
+    out.update(banana_U0=Ub, banana_Gamma=ban.Gamma, banana_Uall=np.array(eb.Uall), banana_Gall=np.array(eb.Gall),
+               banana_t=np.array(eb.metrics["t"]), banana_next_normal=np.random.normal(0, 1, 3))
     np.savez_compressed(os.path.join(HERE, "resume_case.npz"), **out)
     print("Uall", out["Uall"].shape, "t", out["metrics"][4])
 

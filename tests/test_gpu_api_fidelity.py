@@ -37,6 +37,23 @@ def test_resumed_run_matches_the_real_reference():
     assert np.abs(s.Ustar - g["Ustar"]).max() / scale < 1e-8 and np.allclose(s.Gstar, g["Gstar"], rtol=1e-6, atol=1e-8 * scale)
 
 
+@pytest.mark.parametrize("fused", [True, False])
+def test_banana_run_consumes_the_reference_random_stream(fused):
+    """The reference's banana model draws two normals per evaluation even with its noise switched off (ces/utils.py:122),
+    interleaved with the update noise of a seeded run: sampling.run on the device model reproduces the REAL reference's
+    trace and leaves the generator in the same state (golden: tests/golden/make_golden_resume.py)."""
+    g = np.load(os.path.join(HERE, "golden", "resume_case.npz"))
+    s = calibrate.sampling(2, 2, 30)
+    s.ustar, s.mu, s.sigma, s.T, s.fused_run = np.array([[0.4], [1.0]]), np.zeros((2, 1)), 9.0 * np.eye(2), 4, fused
+    np.random.seed(8)
+    s.run(np.array([0.4, 0.3]), g["banana_U0"], cutils.banana(), g["banana_Gamma"], None, t_tol=1e9)
+    assert s.Uall.shape == g["banana_Uall"].shape
+    assert np.abs(s.Uall - g["banana_Uall"]).max() / np.abs(g["banana_Uall"]).max() < 1e-8
+    assert np.abs(s.Gall - g["banana_Gall"]).max() / np.abs(g["banana_Gall"]).max() < 1e-8
+    assert np.allclose(s.metrics["t"], g["banana_t"], rtol=1e-8, atol=0)
+    assert np.array_equal(np.random.normal(0, 1, 3), g["banana_next_normal"])
+
+
 @pytest.mark.parametrize("J,d,k", [(60, 3, 7), (6000, 40, 24)])
 def test_online_save_and_trace_files_hold_the_loop_states(tmp_path, J, d, k):
     """save_online=True writes ensemble_NNNN / Gensemble_NNNN (.npy) + metrics.pkl per iteration (ces/calibrate.py:371-385,

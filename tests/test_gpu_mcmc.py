@@ -1,0 +1,92 @@
+"""MCMC.model_mh on the device (ces_b200/sample.py, csrc/mcmc.cu) against chains of the REAL reference
+(ces/sample.py:121-196; tests/golden/make_golden_mcmc.py): same samples, same acceptance rate, same state of numpy's
+global generator afterwards -- the kernel consumes the MT19937 stream the reference's np.random.normal / uniform calls
+would have consumed -- for random walk and pCN, enka-scaled and fixed proposals, dense Gamma, the resume path, all four
+map models."""
+import os
+
+import numpy as np
+import pytest
+from scipy.stats import multivariate_normal
+
+pytestmark = pytest.mark.gpu
+
+from ces_b200 import calibrate, sample as csample, utils as cutils  # noqa: E402
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mcmc_cases.npz"))
+
+
+def _setup(name):
+    c = {key: G["%s/%s" % (name, key)] for key in ("y", "Gamma", "Ustar", "prior_mean", "prior_cov")}
+    kind = str(G["%s/kind" % name])
+    p, J = c["Ustar"].shape
+    enka = calibrate.sampling(p, c["y"].shape[0], J)
+    enka.Ustar = c["Ustar"]
+    model = {"lineal": lambda: cutils.lineal(G["%s/A" % name]), "elliptic": cutils.elliptic, "banana": cutils.banana}[kind]()
+    prior = multivariate_normal(c["prior_mean"], c["prior_cov"])
+    kw = {}
+    if str(G["%s/update" % name]):
+        kw = {"update": str(G["%s/update" % name]), "beta": float(G["%s/beta" % name])}
+    mc = csample.MCMC()
+    mc.y_obs = c["y"]
+    return mc, model, prior, enka, c["Gamma"], float(G["%s/delta" % name]), bool(G["%s/scaling" % name]), kw, int(G["%s/n" % name])
+
+
+def _state_equal(name, tag):
+    st = np.random.get_state()
+    return (np.array_equal(st[1], G["%s/%s_key" % (name, tag)]) and [st[2], st[3]] == list(G["%s/%s_pos" % (name, tag)])
+            and (st[3] == 0 or abs(st[4] - float(G["%s/%s_gauss" % (name, tag)])) <= 1e-14 * max(1.0, abs(st[4]))))
+
+
+@pytest.mark.parametrize("name", [str(n) for n in G["names"]])
+def test_model_mh_reproduces_the_reference_chain(name):
+    mc, model, prior, enka, Gamma, delta, scaling, kw, n = _setup(name)
+    np.random.seed(13)
+    mc.model_mh(model, n, prior, enka, Gamma, delta=delta, enka_scaling=scaling, **kw)
+    want = G["%s/samples" % name]
+    assert mc.samples.shape == want.shape == (enka.p, n + 1)
+    scale = np.abs(want).max()
+    assert np.abs(mc.samples - want).max() / scale < 1e-10, name          # every accept decision and every state
+    assert abs(mc.accept - float(G["%s/accept" % name])) < 1e-12
+    assert _state_equal(name, "state1")                                       # the generator is where the reference leaves it
+    # second call on the same object: continues from the last sample (:156-164)
+    mc.model_mh(model, 50, prior, enka, Gamma, delta=delta, enka_scaling=scaling, **kw)
+    want2 = G["%s/samples_resumed" % name]
+    assert mc.samples.shape == want2.shape == (enka.p, n + 51)
+    assert np.abs(mc.samples - want2).max() / scale < 1e-10
+    assert abs(mc.accept - float(G["%s/accept_resumed" % name])) < 1e-12 and _state_equal(name, "state2")
+
+
+def test_many_chains_sample_the_linear_gaussian_posterior():
+    """n_chains independent device chains (Philox noise) beside the reference's one: pooled, they reproduce the analytic
+    posterior of the linear-Gaussian problem (mean and covariance)."""
+    name = "lineal_rw"
+    mc, model, prior, enka, Gamma, delta, scaling, kw, n = _setup(name)
+    A, y = G["%s/A" % name], G["%s/y" % name]
+    post_cov = np.linalg.inv(A.T @ np.linalg.solve(Gamma, A) + np.linalg.inv(prior.cov))
+    post_mean = post_cov @ (A.T @ np.linalg.solve(Gamma, y) + np.linalg.solve(prior.cov, prior.mean))
+    np.random.seed(13)
+    mc.model_mh(model, 3000, prior, enka, Gamma, delta=0.15, enka_scaling=False, n_chains=256, seed=5)
+    ch = mc.samples_chains
+    assert ch.shape == (256, 2, 3001) and mc.accept_chains.shape == (256,) and np.all(mc.accept_chains > 0.05)
+    pooled = ch[:, :, 1000:].transpose(1, 0, 2).reshape(2, -1)
+    assert np.abs(pooled.mean(axis=1) - post_mean).max() < 0.02
+    ratio = np.cov(pooled) / post_cov
+    assert np.all(np.abs(np.diag(ratio) - 1.0) < 0.15)
+    # chain 0 is still the reference-stream chain; the others differ from it and from each other
+    assert not np.array_equal(ch[1], ch[2]) and np.array_equal(ch[0], mc.samples)
+
+
+def test_model_mh_refuses_what_it_does_not_cover():
+    mc, model, prior, enka, Gamma, delta, scaling, kw, n = _setup("lineal_rw")
+
+    class Host(object):
+        type = "map"
+
+        def __call__(self, theta):
+            return theta
+
+    with pytest.raises(NotImplementedError):
+        mc.model_mh(Host(), 10, prior, enka, Gamma)
+    with pytest.raises(NotImplementedError):
+        mc.gp_mh(enka, 10, prior)
