@@ -879,17 +879,17 @@ def main():
     ctx.close()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the D GEMM from the committed ncu capture
-# (profiles/); None until a capture for that workload exists.
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the D GEMM, from the committed `ncu --set full` captures of
+# round 2 (tools/gemm_traffic.py: the same kernel, operands and rasterisation as the step's launch).
 TRAFFIC_BYTES = {
-    # profiles/r01_gemm_raster_sweep.csv (group 16, serpentine K): 9.53 GB read + 2.14 GB written for the 16384 x 16384 x 4096 launch
+    # profiles/r02_ncu_full_gemm_d_cfg3.csv: 9.59 GB read + 2.14 GB written for the 16384 x 16384 x 4096 launch (60.41 ms)
     # (algorithmic: E 0.54 + W 0.54 + D 2.15 GB; the excess is E/W panels streamed once per wave of 148 tiles: a wave's
-    # unique footprint, ~100 MB, fills the L2, so there is no cross-wave reuse; 3 % of HBM bandwidth, duration unchanged)
-    "cfg3": 11.67e9,
-    # profiles/r01_ncu_full_gemm_d_target.csv: 56.98 GB read + 8.59 GB written per 65536 x 16384 x 4096 panel launch
-    # (algorithmic: E 2.15 + W panel 0.54 + D panel 8.59 GB), same mechanism, 3.3 % of HBM bandwidth; captured before
-    # the serpentine traversal (-23 % reads at cfg3)
-    "target": 65.57e9,
+    # unique footprint, ~100 MB, fills the L2, so there is no cross-wave reuse; L2 hit rate 83.8 %, 3 % of HBM bandwidth)
+    "cfg3": 11.73e9,
+    # profiles/r02_ncu_full_gemm_d_target.csv: 42.69 GB read + 8.59 GB written per 65536 x 16384 x 4096 panel launch
+    # (241.03 ms; algorithmic: E 2.15 + W panel 0.54 + D panel 8.59 GB), same mechanism; the serpentine traversal of the
+    # contraction axis took the reads from 56.98 GB (round 1) to 42.69 GB
+    "target": 51.28e9,
 }
 
 if __name__ == "__main__":

@@ -109,7 +109,12 @@ class model(object):
         self.model_name = 'darcy-flow'
         self.type = 'map'
         self.flag_noise = False
-        self.tol = 1e-13            # relative residual of the CG solve (the reference solves directly)
+        # Relative residual (in the preconditioner's norm) at which the CG solve stops; the reference solves directly.
+        # Measured on 64^2 / 96^2 / 128^2 fields at prior scales 1-10 (tools/darcy_tol_experiment.py): the error against the
+        # sparse direct solve is 0.2-0.35 x tol, uniformly.  1e-10 keeps the field within 3e-11 of the direct solve -- 30 x
+        # inside the 1e-9 parity bound of tests/test_gpu_darcy.py -- for 22 % fewer iterations than 1e-13 (set it back to
+        # 1e-13 for direct-solver accuracy).
+        self.tol = 1e-10
         self.max_iter = 0           # 0: the library default, 40 N iterations
         self._dev = None
 

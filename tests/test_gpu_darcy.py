@@ -8,7 +8,7 @@ pytestmark = pytest.mark.gpu
 from ces_b200 import calibrate, darcy as cdarcy  # noqa: E402
 from oracle import darcy_oracle as do, eks_oracle as eo  # noqa: E402
 
-TOL = 1e-9      # iterative solve (relative residual 1e-13) vs sparse direct
+TOL = 1e-9      # iterative solve (default relative residual 1e-10: measured error 2-3.5e-11) vs sparse direct
 
 
 def _rel(a, b):
@@ -132,12 +132,14 @@ def test_solver_statistics_and_coarse_level(monkeypatch):
     rng = np.random.default_rng(11)
     U = rng.standard_normal((64, 6))
     m = cdarcy.model_trunc(Nmesh=64, p=64)
+    m.tol = 1e-13                        # (the default 1e-10 leaves each solution 3e-11 from the direct solve)
     full = m.solve_ensemble(U, full_solution=True)
     members, total, ms = m.last_stats()
     assert members == 6 and ms > 0.0 and m.last_iterations <= total <= 6 * m.last_iterations
     its_two_level = total
     monkeypatch.setenv("CES_DARCY_COARSE", "0")
     j = cdarcy.model_trunc(Nmesh=64, p=64)
+    j.tol = 1e-13
     jac = j.solve_ensemble(U, full_solution=True)
     assert j.last_stats()[1] > 1.8 * its_two_level            # Jacobi alone needs ~2.5x the iterations at 64 x 64
     assert _rel(full, jac) < 1e-10
@@ -158,7 +160,7 @@ def test_iteration_counts_match_the_pcg_oracle(N, p, scale):
     ref = do.ModelTrunc(Nmesh=N, p=p)
     m.solve_ensemble(U, full_solution=True)
     _, total, _ = m.last_stats()
-    want = sum(dp.solve(ref.eval_rf(U[:, j]))[1] for j in range(members))
+    want = sum(dp.solve(ref.eval_rf(U[:, j]), tol=m.tol)[1] for j in range(members))
     assert abs(total - want) <= max(3, 0.02 * want), (total, want)
 
 
