@@ -52,13 +52,17 @@ struct ces_handle_s {
     int64_t run_ws_len = 0;
     int hb_nchunk = 1, hb_formulation = 0;   // state of a host step in progress (ces_host_begin ... ces_host_update)
     bool hb_have_xi = false;
-    int64_t hb_bound[5] = {0, 0, 0, 0, 0};
+    int64_t hb_bound[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    bool hb_timed = false;
+    int hb_nchunk_prev = 1;
     cudaStream_t aux_st = nullptr;      // chol(C^uu) runs here, hidden behind the D / V GEMMs of the main stream
     cudaEvent_t cuu_ready = nullptr, chol_done = nullptr;
     bool chol_pending = false;
     cudaStream_t copy_st = nullptr;     // ces_step_host: uploads G (row chunks), U and xi while the main stream computes
     cudaEvent_t copy_ev = nullptr, start_ev = nullptr, u_ev = nullptr;
-    cudaEvent_t g_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t g_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t up_begin = nullptr;     // timing pair around the upload of G: the measured host->device rate sizes the next call's chunks
+    double h2d_gbs = 0.0;               // 0: not measured yet
     cudaStream_t out_st = nullptr;      // phase 4: downloads finished column chunks of U_next while the next chunk computes
     cudaEvent_t out_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::vector<void*> allocs;
@@ -254,6 +258,7 @@ int ces_destroy(ces_handle_t h) {
     if (h->start_ev) cudaEventDestroy(h->start_ev);
     if (h->u_ev) cudaEventDestroy(h->u_ev);
     for (cudaEvent_t e : h->g_ev) if (e) cudaEventDestroy(e);
+    if (h->up_begin) cudaEventDestroy(h->up_begin);
     for (cudaEvent_t e : h->out_ev) if (e) cudaEventDestroy(e);
     if (h->copy_st) cudaStreamDestroy(h->copy_st);
     if (h->out_st) { cudaStreamSynchronize(h->out_st); cudaStreamDestroy(h->out_st); }
@@ -967,7 +972,8 @@ static int host_staging(ces_handle_t h) {
         CES_CUDA(cudaEventCreateWithFlags(&h->copy_ev, cudaEventDisableTiming));
         CES_CUDA(cudaEventCreateWithFlags(&h->start_ev, cudaEventDisableTiming));
         CES_CUDA(cudaEventCreateWithFlags(&h->u_ev, cudaEventDisableTiming));
-        for (cudaEvent_t& e : h->g_ev) CES_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (cudaEvent_t& e : h->g_ev) CES_CUDA(cudaEventCreate(&e));          // (timing enabled: the last one closes the rate measurement)
+        CES_CUDA(cudaEventCreate(&h->up_begin));
     }
     return CES_OK;
 }
@@ -979,28 +985,77 @@ static cudaError_t host_h2d(ces_handle_t h, double* dst, const double* src, int6
     return cudaMemcpy2DAsync(dst, ld * sizeof(double), src, w * sizeof(double), w * sizeof(double), rows, cudaMemcpyHostToDevice, s);
 }
 
+// Row chunks of the G upload of a host step: bounds[0..n] (n <= 8 chunks), returns n.  A PURE function of its arguments --
+// every rank of a column-sharded step must arrive at the same chunks, because the caller all-reduces the means slice by
+// slice: nothing rank-local (measured rates, this rank's column count) may enter when nranks > 1.
+//   rho = time of the first-panel GEMM per row of G (2 J_l min(panel, J_l) flop at ~36 TF/s)
+//       / time of the upload per row (8 J_l bytes at h2d_gbs; 0 = nominal for the process count, measured on this pool:
+//         55 GB/s for 1-2 processes, ~40 for 4, ~21 each when eight upload at once).
+// A first chunk of k/32 rows is the only exposed transfer; each following chunk may be rho times the previous one (its
+// upload hides behind the previous chunk's GEMM): three chunks at rho ~ 6 (one GPU, 16384-column panel).  When that does
+// not reach k within 8 chunks (uploads as slow as the GEMM: eight ranks) the rest is split evenly, so the contraction keeps
+// pace with the arrival and only the last seventh remains when the upload ends.  Small shapes: one chunk.
+int ces_host_chunk_schedule(int64_t k, int64_t J_local, int64_t panel, int nranks, double h2d_gbs, int64_t* bound /* [9] */) {
+    if (!bound || k < 1) return 0;
+    bound[0] = 0;
+    for (int i = 1; i < 9; ++i) bound[i] = k;
+    if (k < 256 || J_local < 2048) return 1;
+    const double panel0 = (double)(panel < J_local ? panel : J_local);
+    const double t_gemm = 2.0 * (double)J_local * panel0 / 36.0e12;
+    double gbs = h2d_gbs;
+    if (!(gbs > 1.0)) gbs = nranks <= 2 ? 55.0 : (nranks <= 4 ? 40.0 : 21.0);
+    const double t_up = 8.0 * (double)J_local / (gbs * 1e9);
+    double rho = 0.9 * t_gemm / t_up;
+    if (rho > 8.0) rho = 8.0;
+    const int64_t first = round_up(k / 32 > 16 ? k / 32 : 16, 16);
+    constexpr int kMaxChunks = 8;
+    int n = 1;
+    int64_t at = first, size = first;
+    bound[1] = first;
+    bool fits = false;
+    if (rho >= 1.5) {
+        while (n < kMaxChunks) {
+            size = round_up((int64_t)(size * rho), 16);
+            if (at + size >= k || n == kMaxChunks - 1) {
+                fits = (at + size >= k) || (k - at) <= (int64_t)(size * 1.2);
+                bound[++n] = k;
+                at = k;
+                break;
+            }
+            at += size;
+            bound[++n] = at;
+        }
+    }
+    if (!fits) {
+        const int64_t each = round_up(ceil_div(k - first, kMaxChunks - 1), 16);
+        n = 1;
+        at = first;
+        while (at < k && n < kMaxChunks) { at = at + each < k ? at + each : k; bound[++n] = at; }
+        bound[n] = k;
+    }
+    for (int i = n + 1; i < 9; ++i) bound[i] = k;
+    return n;
+}
+
 int ces_host_begin(ces_handle_t h, int rule, int formulation, const double* U, const double* G, const double* xi,
-                   int* nchunks_out, int64_t* bounds_out /* [5] */) {
+                   int* nchunks_out, int64_t* bounds_out /* [9] */) {
     CES_TRY(valid(h, true));
     if (rule < CES_RULE_EKS || rule > CES_RULE_EKI) return fail(CES_ERR_INVALID, "unknown update rule %s%lld", "", rule);
     if (formulation != CES_FORM_INTERACTION && formulation != CES_FORM_FACTORED) return fail(CES_ERR_INVALID, "unknown formulation%s", "");
     if ((!U || !G) && h->cols > 0) return fail(CES_ERR_INVALID, "ces_host_begin: null pointer%s", "");
     CES_TRY(host_staging(h));
     const int64_t p = h->p, k = h->k, ld = h->ldJ, w = h->cols;
-    // ---- uploads, all on the copy stream, in the order the main stream needs them: G in row chunks, U, xi.
-    // Row means are per row over the particles, so a row chunk of G can be summed and centred as soon as it has
-    // landed, and the D GEMM of the first column panel (own block) contracts over the rows received so far (later chunks
-    // accumulate with beta = 1).  With chunks of k/32, 7k/32 and 3k/4 rows every upload after the first hides behind the
-    // GEMM of the previous chunk (per row of G the GEMM takes 2 J_l min(panel, J_l) flop at ~36 TF/s, the upload 8 J_l
-    // bytes at ~55 GB/s: a factor ~6 at a 16384-column panel), so the only exposed transfer is the first k/32 rows.
-    // Dense Gamma (W = Gamma^-1 R needs all of R), the factored formulation and small shapes use one chunk.
-    int nchunk = 1;
+    // ---- uploads, all on the copy stream, in the order the main stream needs them: G in row chunks (ces_host_chunk_schedule),
+    // U, xi.  Row means are per row over the particles, so a row chunk of G can be summed and centred as soon as it has landed,
+    // and the D GEMM of the first column panel (own block) contracts over the rows received so far (beta = 1 after the first).
     int64_t* bound = h->hb_bound;
-    bound[0] = 0; bound[1] = bound[2] = bound[3] = bound[4] = k;
-    if (formulation == CES_FORM_INTERACTION && h->gamma_diag && k >= 256 && h->Jl >= 2048) {
-        nchunk = 3;
-        bound[1] = round_up(k / 32, 16);
-        bound[2] = round_up(k / 4, 16);
+    int nchunk = 1;
+    bound[0] = 0;
+    for (int i = 1; i < 9; ++i) bound[i] = k;
+    if (formulation == CES_FORM_INTERACTION && h->gamma_diag) {
+        double gbs = 0.0;                       // several ranks: the nominal rate of the process count (see the schedule)
+        if (h->nranks == 1 && h->h2d_gbs > 1.0) gbs = h->h2d_gbs;
+        nchunk = ces_host_chunk_schedule(k, h->Jl, h->panel, h->nranks, gbs, bound);
     }
     h->hb_nchunk = nchunk;
     h->hb_formulation = formulation;
@@ -1008,12 +1063,22 @@ int ces_host_begin(ces_handle_t h, int rule, int formulation, const double* U, c
     mark(h, "host:begin");
     CES_CUDA(cudaEventRecord(h->start_ev, h->st));                // after the previous step's readers of the staging buffers
     CES_CUDA(cudaStreamWaitEvent(h->copy_st, h->start_ev, 0));
-    static const char* up_names[4] = {"upload:G0", "upload:G1", "upload:G2", "upload:G3"};
+    // the rate of the previous call's G upload (its events have completed: that call ended with a synchronisation)
+    if (h->hb_timed) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->up_begin, h->g_ev[h->hb_nchunk_prev - 1]) == cudaSuccess && ms > 0.05f)
+            h->h2d_gbs = (double)k * (double)w * 8.0 / (ms * 1e-3) * 1e-9;
+        else cudaGetLastError();
+    }
+    static const char* up_names[8] = {"upload:G0", "upload:G1", "upload:G2", "upload:G3", "upload:G4", "upload:G5", "upload:G6", "upload:G7"};
+    CES_CUDA(cudaEventRecord(h->up_begin, h->copy_st));
     for (int c = 0; c < nchunk; ++c) {
         CES_CUDA(host_h2d(h, h->stage_G + bound[c] * ld, G + bound[c] * w, bound[c + 1] - bound[c], h->copy_st));
         CES_CUDA(cudaEventRecord(h->g_ev[c], h->copy_st));
         mark(h, up_names[c], h->copy_st);
     }
+    h->hb_timed = w > 0;
+    h->hb_nchunk_prev = nchunk;
     CES_CUDA(host_h2d(h, h->stage_U, U, p, h->copy_st));
     CES_CUDA(cudaEventRecord(h->u_ev, h->copy_st));
     mark(h, "upload:U", h->copy_st);
@@ -1024,7 +1089,7 @@ int ces_host_begin(ces_handle_t h, int rule, int formulation, const double* U, c
     }
     h->last_rule = rule;
     if (nchunks_out) *nchunks_out = nchunk;
-    if (bounds_out) for (int i = 0; i < 5; ++i) bounds_out[i] = bound[i];
+    if (bounds_out) for (int i = 0; i < 9; ++i) bounds_out[i] = bound[i];
     return CES_OK;
 }
 
@@ -1056,8 +1121,8 @@ int ces_host_interact_chunk(ces_handle_t h, int chunk) {
     const int64_t r0 = h->hb_bound[chunk], nr = h->hb_bound[chunk + 1] - r0;
     if (h->hb_nchunk > 1) {
         // own block, first column panel: contract over the rows received so far
-        static const char* ck[4] = {"centred:G0", "centred:G1", "centred:G2", "centred:G3"};
-        static const char* dk[4] = {"D0:chunk0", "D0:chunk1", "D0:chunk2", "D0:chunk3"};
+        static const char* ck[8] = {"centred:G0", "centred:G1", "centred:G2", "centred:G3", "centred:G4", "centred:G5", "centred:G6", "centred:G7"};
+        static const char* dk[8] = {"D0:chunk0", "D0:chunk1", "D0:chunk2", "D0:chunk3", "D0:chunk4", "D0:chunk5", "D0:chunk6", "D0:chunk7"};
         InteractRange rg;
         rg.c_begin = 0; rg.c_end = h->panel < h->Jl ? h->panel : h->Jl; rg.k_lo = r0; rg.k_hi = r0 + nr;
         rg.do_v = false; rg.reset = (chunk == 0); rg.finish = false;

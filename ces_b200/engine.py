@@ -474,7 +474,7 @@ class Engine(object):
             if resolve is None and formulation == "interaction":
                 r = _lib.RULES[rule]
                 ts = _lib.TS_FIXED if fixed_h is not None else _lib.TS_FROBENIUS
-                nch, bounds = ctypes.c_int(), (ctypes.c_int64 * 5)()
+                nch, bounds = ctypes.c_int(), (ctypes.c_int64 * 9)()
                 _lib.check(lib.ces_host_begin(h, r, 0, ptr(U), ptr(G), ptr(xi), ctypes.byref(nch), bounds))
                 sums, k, p = self.buffer("sums"), self.k, self.p
                 last = nch.value - 1

@@ -166,8 +166,8 @@ int ces_timeline_mark(ces_handle_t h, const char* name);
 int ces_timeline_read(ces_handle_t h, char* names, int64_t names_cap, double* ms, int64_t ms_cap, int64_t* count);
 /* The host step in pieces, for column-sharded callers (nranks > 1; ces_step_host is exactly this sequence with no
  * collectives).  Host arrays are this rank's dense shards: U_host, xi_host p x cols_local, G_host k x cols_local.
- *   ces_host_begin         queues every upload on the copy stream (G in *nchunks row chunks with bounds[0..nchunks],
- *                          then U, then xi) and returns at once
+ *   ces_host_begin         queues every upload on the copy stream (G in *nchunks <= 8 row chunks with bounds[0..nchunks],
+ *                          sized from the host->device rate measured on the previous call; then U, then xi) and returns
  *   for c in chunks:       ces_host_sums_g(c)     row sums of the chunk          [all-reduce "sums"[bounds[c]:bounds[c+1]]]
  *                          ces_host_centre_g(c, interact)   E, W rows; interact != 0: ces_host_interact_chunk(c) at once
  *                          ces_host_interact_chunk(c)       with several chunks: the own block's first D panel contracted
@@ -180,8 +180,11 @@ int ces_timeline_read(ces_handle_t h, char* names, int64_t names_cap, double* ms
  *   [ces_phase4a_drift for aldi_constant                                              all-reduce(max) "scalars"[5:6]]
  *   ces_host_update        waits for xi, assembles U_next and downloads this rank's p x cols_local block into
  *                          Uout_host in overlapped column chunks; returns hk and the diagnostics like ces_phase4_update */
+/* The row chunks ces_host_begin will use (bounds[0..n], returns n <= 8): a pure function, identical on every rank (no
+ * handle, no device).  h2d_gbs <= 0: the nominal host->device rate for `nranks` processes. */
+int ces_host_chunk_schedule(int64_t k, int64_t J_local, int64_t panel, int nranks, double h2d_gbs, int64_t* bounds /* [9] */);
 int ces_host_begin(ces_handle_t h, int rule, int formulation, const double* U_host, const double* G_host,
-                   const double* xi_host, int* nchunks_out, int64_t* bounds_out /* [5] */);
+                   const double* xi_host, int* nchunks_out, int64_t* bounds_out /* [9] */);
 int ces_host_sums_g(ces_handle_t h, int chunk);
 int ces_host_centre_g(ces_handle_t h, int chunk, int interact);
 int ces_host_interact_chunk(ces_handle_t h, int chunk);

@@ -69,3 +69,32 @@ def test_sass_uses_fp64_tensor_cores_and_tma():
     assert "DMMA.8x8x4" in sass
     assert "UTMALDG.2D" in sass
     assert "arch = sm_100a" in sass
+
+
+def test_host_chunk_schedule_is_rank_independent_and_well_formed():
+    """ces_host_chunk_schedule decides how the G upload of a host step is cut into row chunks.  Every rank of a column-sharded
+    step all-reduces the means chunk by chunk, so all ranks must compute the SAME chunks: the function takes no rank, no
+    column count and (for nranks > 1) no measured rate -- a rank-local measurement made two ranks disagree on the chunk
+    count once and the step hung in its all-reduces.  Host-only code: runs without a GPU."""
+    from ces_b200 import _lib
+
+    lib = _lib.load()
+
+    def sched(k, Jl, panel, nranks, gbs=0.0):
+        b = (ctypes.c_int64 * 9)()
+        n = lib.ces_host_chunk_schedule(k, Jl, panel, nranks, gbs, b)
+        return n, list(b)
+
+    for (k, Jl, panel, nranks) in [(4096, 65536, 16384, 1), (4096, 32768, 16384, 2), (4096, 16384, 16384, 4),
+                                   (4096, 8192, 8192, 8), (4096, 2048, 2048, 8), (16384, 8192, 8192, 8), (272, 2150, 1536, 2),
+                                   (300, 5000, 5000, 3), (255, 65536, 16384, 1), (4096, 2047, 2047, 4)]:
+        n, b = sched(k, Jl, panel, nranks)
+        assert 1 <= n <= 8 and b[0] == 0 and b[n] == k and all(b[i] == k for i in range(n, 9)), (k, Jl, nranks, n, b)
+        assert all(b[i] < b[i + 1] for i in range(n)) and all(b[i] % 16 == 0 for i in range(n)), b
+        if k < 256 or Jl < 2048:
+            assert n == 1
+        assert sched(k, Jl, panel, nranks) == (n, b)                  # deterministic
+    # one GPU, fast uploads: three geometric chunks; eight ranks, slow uploads: an even split
+    assert sched(4096, 65536, 16384, 1)[0] == 3 and sched(4096, 8192, 8192, 8)[0] == 8
+    # a measured rate only matters on a single GPU path; the nominal one is used otherwise by the caller
+    assert sched(4096, 65536, 16384, 1, 55.0)[0] == 3 and sched(4096, 65536, 16384, 1, 5.0)[0] > 3
