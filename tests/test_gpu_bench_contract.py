@@ -63,7 +63,8 @@ def test_cfg1_run_line():
     d = json.loads(lines[0])
     for key in REQUIRED + ("roofline",):
         assert key in d, key
-    assert d["steps"] == 1000 and d["config"]["J"] == 100 and d["value"] > 0 and d["e2e"]["value"] > 0 and d["gpu_launches"] >= 1000
+    # (the whole run is ONE launch of small_run_kernel: forward map + update + stopping rule per iteration on the device)
+    assert d["steps"] == 1000 and d["config"]["J"] == 100 and d["value"] > 0 and d["e2e"]["value"] > 0 and d["gpu_launches"] >= 1
     # the run converges to the analytic posterior mean of the notebook problem (linear.ipynb:695-697)
     assert abs(d["posterior_mean"][0] + 1.0367) < 0.1 and abs(d["posterior_mean"][1] - 2.0870) < 0.1
 
