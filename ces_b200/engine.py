@@ -145,6 +145,66 @@ def run_phases(phases, buffer, comm, p, k, rule, resolve=None, formulation="inte
     phases["update"](keep)
 
 
+def run_host_phases(phases, buffer, comm, p, k, rule, bounds):
+    """The pipelined HOST step of a column shard (include/ces_b200.h: "the host step in pieces") with this rank's
+    collectives in between.  ``bounds`` = the row chunks of the G upload (``ces_host_chunk_schedule``: identical on every
+    rank -- the means are all-reduced slice by slice, so every rank must cut the same chunks):
+
+        for chunk c:  sums_g(c) -> all-reduce(sum) "sums"[bounds[c]:bounds[c+1]] -> centre_g(c) [+ interact_chunk(c)]
+        sums_u        -> all-reduce(sum) "sums"[k:k+p]
+        centre_u      -> all-reduce(sum) "cuu";  gathers of "e_all" / "ut_all" started (peer pulls, or all-gathers)
+        interact_chunk(last), interact_own   (run while the other ranks' blocks arrive)
+        interact_rest -> all-reduce(sum) "scalars"[0:5]
+        [drift        -> all-reduce(max) "scalars"[5:6]]          aldi_constant only
+        update
+
+    The last chunk's share of the own block's D panel is deferred until the gathers have been started, so they run under
+    it.  ``phases`` maps the names to callables (the engine passes the ctypes calls of the library;
+    tests/test_multirank_gloo.py passes a numpy stand-in and runs this over gloo without a GPU)."""
+    dist, group, rank = comm
+    mark = phases.get("mark", lambda name: None)
+    sums = buffer("sums")
+    nchunks = len(bounds) - 1
+    last = nchunks - 1
+    for c in range(nchunks):
+        phases["sums_g"](c)
+        dist.all_reduce(sums[0, bounds[c]:bounds[c + 1]], group=group)
+        phases["centre_g"](c, c != last)
+    phases["sums_u"]()
+    dist.all_reduce(sums[0, k:k + p], group=group)
+    phases["centre_u"]()
+    dist.all_reduce(buffer("cuu"), group=group)
+    mark("allreduce:cuu:done")
+    e_all, ut_all = buffer("e_all"), buffer("ut_all")
+    e_own, ut_own = e_all[rank * k:(rank + 1) * k], ut_all[rank * p:(rank + 1) * p]
+    if "peer_gather" in phases:
+        phases["peer_gather"]()
+        phases["interact_chunk"](last)
+        phases["interact_own"]()
+        phases["peer_wait"]()
+    elif dist.get_backend(group) == "nccl":
+        works = [dist.all_gather_into_tensor(e_all, e_own, group=group, async_op=True),
+                 dist.all_gather_into_tensor(ut_all, ut_own, group=group, async_op=True)]
+        phases["interact_chunk"](last)
+        phases["interact_own"]()
+        for wk in works:
+            wk.wait()
+    else:
+        dist.all_gather_into_tensor(e_all, e_own.clone(), group=group)
+        dist.all_gather_into_tensor(ut_all, ut_own.clone(), group=group)
+        phases["interact_chunk"](last)
+        phases["interact_own"]()
+    mark("gather:e,ut:waited")
+    phases["interact_rest"]()
+    scal = buffer("scalars")
+    dist.all_reduce(scal[0, 0:5], group=group)
+    mark("allreduce:scalars:done")
+    if rule == "aldi_constant":
+        phases["drift"]()
+        dist.all_reduce(scal[0, 5:6], op=dist.ReduceOp.MAX, group=group)
+    phases["update"]()
+
+
 @contextlib.contextmanager
 def stream_guard(torch, lib_stream):
     """A library handle launches on the stream that was current when it was created.  Torch work issued around it
@@ -476,48 +536,25 @@ class Engine(object):
                 ts = _lib.TS_FIXED if fixed_h is not None else _lib.TS_FROBENIUS
                 nch, bounds = ctypes.c_int(), (ctypes.c_int64 * 9)()
                 _lib.check(lib.ces_host_begin(h, r, 0, ptr(U), ptr(G), ptr(xi), ctypes.byref(nch), bounds))
-                sums, k, p = self.buffer("sums"), self.k, self.p
-                last = nch.value - 1
-                for c in range(nch.value):
-                    _lib.check(lib.ces_host_sums_g(h, c))
-                    dist.all_reduce(sums[0, bounds[c]:bounds[c + 1]], group=group)
-                    # the last chunk's share of the own block's D panel is deferred until the gathers of the other
-                    # ranks' blocks have been started: they then run under it instead of after it
-                    _lib.check(lib.ces_host_centre_g(h, c, 0 if c == last else 1))
-                _lib.check(lib.ces_host_sums_u(h))
-                dist.all_reduce(sums[0, k:k + p], group=group)
-                _lib.check(lib.ces_host_centre_u(h))
-                dist.all_reduce(self.buffer("cuu"), group=group)
-                self.mark("allreduce:cuu:done")
-                e_all, ut_all = self.buffer("e_all"), self.buffer("ut_all")
-                e_own, ut_own = e_all[self.rank * k:(self.rank + 1) * k], ut_all[self.rank * p:(self.rank + 1) * p]
+                fh = float(fixed_h) if fixed_h is not None else 0.0
+                out_ptr = host.data_ptr() if self.cols else None
+                phases = {
+                    "sums_g": lambda c: _lib.check(lib.ces_host_sums_g(h, c)),
+                    "centre_g": lambda c, interact: _lib.check(lib.ces_host_centre_g(h, c, 1 if interact else 0)),
+                    "interact_chunk": lambda c: _lib.check(lib.ces_host_interact_chunk(h, c)),
+                    "sums_u": lambda: _lib.check(lib.ces_host_sums_u(h)),
+                    "centre_u": lambda: _lib.check(lib.ces_host_centre_u(h)),
+                    "interact_own": lambda: _lib.check(lib.ces_host_interact_own(h)),
+                    "interact_rest": lambda: _lib.check(lib.ces_phase3_blocks(h, r, 1, self.nranks - 1)),
+                    "drift": lambda: _lib.check(lib.ces_phase4a_drift(h, float(switch))),
+                    "update": lambda: _lib.check(lib.ces_host_update(h, ts, fh, out_ptr, ctypes.byref(self._hk), self._met)),
+                    "mark": self.mark,
+                }
                 if self.peer_gather:
-                    _lib.check(lib.ces_peer_gather(h))
-                    _lib.check(lib.ces_host_interact_chunk(h, last))
-                    _lib.check(lib.ces_host_interact_own(h))
-                    _lib.check(lib.ces_peer_gather_wait(h))
-                elif dist.get_backend(group) == "nccl":
-                    works = [dist.all_gather_into_tensor(e_all, e_own, group=group, async_op=True),
-                             dist.all_gather_into_tensor(ut_all, ut_own, group=group, async_op=True)]
-                    _lib.check(lib.ces_host_interact_chunk(h, last))
-                    _lib.check(lib.ces_host_interact_own(h))
-                    for wk in works:
-                        wk.wait()
-                else:
-                    dist.all_gather_into_tensor(e_all, e_own.clone(), group=group)
-                    dist.all_gather_into_tensor(ut_all, ut_own.clone(), group=group)
-                    _lib.check(lib.ces_host_interact_chunk(h, last))
-                    _lib.check(lib.ces_host_interact_own(h))
-                self.mark("gather:e,ut:waited")
-                _lib.check(lib.ces_phase3_blocks(h, r, 1, self.nranks - 1))
-                scal = self.buffer("scalars")
-                dist.all_reduce(scal[0, 0:5], group=group)
-                self.mark("allreduce:scalars:done")
-                if rule == "aldi_constant":
-                    _lib.check(lib.ces_phase4a_drift(h, float(switch)))
-                    dist.all_reduce(scal[0, 5:6], op=dist.ReduceOp.MAX, group=group)
-                _lib.check(lib.ces_host_update(h, ts, float(fixed_h) if fixed_h is not None else 0.0,
-                                               host.data_ptr() if self.cols else None, ctypes.byref(self._hk), self._met))
+                    phases["peer_gather"] = lambda: _lib.check(lib.ces_peer_gather(h))
+                    phases["peer_wait"] = lambda: _lib.check(lib.ces_peer_gather_wait(h))
+                run_host_phases(phases, self.buffer, (dist, group, self.rank), self.p, self.k, rule,
+                                [int(bounds[i]) for i in range(nch.value + 1)])
                 met = {key: float(self._met[i]) for i, key in enumerate(_METRIC_KEYS)}
                 return host.numpy(), float(self._hk.value), met
             # ---- non-default modes: plain uploads (xi on a side stream: only the last phase needs it), device phases

@@ -41,6 +41,91 @@ class NumpyPhases(object):
                 "update": self.update, "peek": self.peek, "cpp": self.cpp, "resolve": self.resolve,
                 "products": self.products, "finish_factored": self.finish_factored, "spectral": self.spectral}
 
+    # ---- the pipelined host step in pieces (ces_host_*; ces_b200.engine.run_host_phases).  Needs a diagonal Gamma: a row
+    # chunk of W = Gamma^-1 (G - y) is then a function of the same rows of G only.
+    def bind_host(self, rule, U, G, xi, bounds, switch=1.0):
+        self.rule, self.U, self.G, self.xi, self.switch, self.fixed_h = rule, U, G, xi, switch, None
+        self.bounds = list(bounds)
+        self.W = np.zeros((self.k, self.cols))
+        self.D_own = np.zeros((self.Jl, self.cols))
+        self.calls = []
+        return {"sums_g": self.h_sums_g, "centre_g": self.h_centre_g, "interact_chunk": self.h_interact_chunk,
+                "sums_u": self.h_sums_u, "centre_u": self.h_centre_u, "interact_own": self.h_interact_own,
+                "interact_rest": self.h_interact_rest, "drift": self.drift, "update": self.update}
+
+    def _rows(self, c):
+        return slice(self.bounds[c], self.bounds[c + 1])
+
+    def h_sums_g(self, c):
+        self.calls.append(("sums_g", c))
+        self.buf["sums"][0, self._rows(c)] = torch.from_numpy(self.G[self._rows(c)].sum(axis=1))
+
+    def h_centre_g(self, c, interact):
+        self.calls.append(("centre_g", c, bool(interact)))
+        k, r = self.k, self._rows(c)
+        means = self.buf["sums"][0, r].numpy() / self.J
+        e_all = self.buf["e_all"].numpy()
+        e_all[self.rank * k + r.start:self.rank * k + r.stop] = 0.0
+        e_all[self.rank * k + r.start:self.rank * k + r.stop, :self.cols] = self.G[r] - means[:, None]
+        self.W[r] = (self.G[r] - self.y[r, None]) / np.diag(self.Gamma)[r, None]
+        if interact:
+            self.h_interact_chunk(c)
+
+    def h_interact_chunk(self, c):
+        self.calls.append(("interact_chunk", c))
+        k, r = self.k, self._rows(c)
+        if len(self.bounds) > 2:            # several chunks: the own block's D panel accumulates over them
+            E = self.buf["e_all"].numpy()[self.rank * k + r.start:self.rank * k + r.stop, :self.Jl]
+            self.D_own += (E.T @ self.W[r]) / self.J
+
+    def h_sums_u(self):
+        k, c = self.k, self.cols
+        E = self.buf["e_all"].numpy()[self.rank * k:(self.rank + 1) * k, :c]
+        R = self.G - self.y[:, None]
+        S = self.buf["scalars"][0].numpy()
+        S[3] = (np.einsum("ij,ij->j", E, E / np.diag(self.Gamma)[:, None]) ** 2).sum()
+        S[4] = (np.einsum("ij,ij->j", R, self.W) ** 2).sum()
+        self.buf["sums"][0, k:] = torch.from_numpy(self.U.sum(axis=1))
+
+    def h_centre_u(self):
+        p, k, c = self.p, self.k, self.cols
+        means = self.buf["sums"][0, k:].numpy() / self.J
+        Ut = self.U - means[:, None]
+        self.Z = np.linalg.solve(self.Sigma0, self.U - self.mu)
+        ut_all = self.buf["ut_all"].numpy()
+        ut_all[self.rank * p:(self.rank + 1) * p] = 0.0
+        ut_all[self.rank * p:(self.rank + 1) * p, :c] = Ut
+        S = self.buf["scalars"][0].numpy()
+        S[1] = (Ut ** 2).sum()
+        S[2] = ((self.U - self.ustar) ** 2).sum()
+        alpha = 1.0 / self.J if self.rule == "eks" else 1.0 / (self.J - 1)
+        C = alpha * (Ut @ Ut.T)
+        if self.rank == 0:
+            C = C + 1e-8 * np.eye(p)
+        cuu = self.buf["cuu"].numpy()
+        cuu[:] = 0.0
+        cuu[:, :p] = C
+
+    def h_interact_own(self):
+        p, k = self.p, self.k
+        self.C = self.buf["cuu"].numpy()[:, :p].copy()
+        if len(self.bounds) <= 2:           # single chunk: the whole own block here
+            E = self.buf["e_all"].numpy()[self.rank * k:(self.rank + 1) * k, :self.Jl]
+            self.D_own = (E.T @ self.W) / self.J
+        Ut = self.buf["ut_all"].numpy()[self.rank * p:(self.rank + 1) * p, :self.Jl]
+        self.V = Ut @ self.D_own
+        self._ssq = (self.D_own ** 2).sum()
+
+    def h_interact_rest(self):
+        p, k = self.p, self.k
+        e_all, ut_all = self.buf["e_all"].numpy(), self.buf["ut_all"].numpy()
+        for i in range(1, self.nranks):
+            s = (self.rank + i) % self.nranks
+            D = (e_all[s * k:(s + 1) * k, :self.Jl].T @ self.W) / self.J
+            self._ssq += (D ** 2).sum()
+            self.V += ut_all[s * p:(s + 1) * p, :self.Jl] @ D
+        self.buf["scalars"][0, 0] = self._ssq
+
     def sums(self):
         s = np.concatenate([self.G.sum(axis=1), self.U.sum(axis=1)])
         self.buf["sums"][0] = torch.from_numpy(s)

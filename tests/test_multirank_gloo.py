@@ -79,3 +79,69 @@ def test_sharded_orchestration_matches_single_process(world, rule, J, ts, t_last
     got = sorted(q.get(timeout=10) for _ in range(world))
     for rank, err, herr, merr in got:
         assert err < 1e-12 and herr < 1e-12 and merr < 1e-12, (rank, err, herr, merr)
+
+
+def _host_worker(rank, world, port, rule, d, k, J, bounds, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from _numpy_phases import NumpyPhases
+        from ces_b200.engine import run_host_phases
+        from oracle import eks_oracle as eo
+
+        pr = eo.linear_gaussian_problem(d, k, J)                       # diagonal Gamma (the pipelined host step's case)
+        ph = NumpyPhases(d, k, J, rank, world, pr["y"], pr["Gamma"], pr["mu"], pr["Sigma0"], pr["ustar"])
+        sl = slice(ph.lo, ph.hi)
+        if bounds == "library":
+            # the chunks the library itself would cut for this shape (a pure host function: needs no GPU)
+            import ctypes
+
+            from ces_b200 import _lib
+
+            b = (ctypes.c_int64 * 9)()
+            n = _lib.load().ces_host_chunk_schedule(k, ph.Jl, ph.ldJ, world, 0.0, b)
+            bounds = [int(b[i]) for i in range(n + 1)]
+        phases = ph.bind_host(rule, pr["U0"][:, sl], pr["G"][:, sl], pr["xi"][:, sl], bounds)
+        run_host_phases(phases, ph.buffer, (dist, None, rank), d, k, rule, bounds)
+        ref = eo.step(rule, pr["y"], pr["U0"], pr["G"], pr["Gamma"], pr["mu"], pr["Sigma0"], pr["ustar"], pr["xi"])
+        err = np.abs(ph.out - ref["Uk"][:, sl]).max() / np.abs(ref["Uk"]).max() if ph.cols else 0.0
+        herr = abs(ph.hk - ref["hk"]) / ref["hk"]
+        merr = max(abs(ph.metrics[m] - ref["metrics"][m]) / abs(ref["metrics"][m]) for m in ph.metrics)
+        # the last chunk's share of the own block is deferred until after the all-reduce of cuu (gathers started first)
+        last = len(bounds) - 2
+        order = [c for c in ph.calls if c[0] != "sums_g"]
+        ok_order = ("centre_g", last, False) in order and order.index(("interact_chunk", last)) > order.index(("centre_g", last, False))
+        q.put((rank, float(err), float(herr), float(merr), len(bounds) - 1, bool(ok_order)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,rule,d,k,J,bounds", [
+    (2, "aldi", 5, 40, 37, [0, 16, 40]), (3, "aldi_constant", 4, 48, 29, [0, 16, 32, 48]), (2, "eks", 5, 33, 26, [0, 33]),
+    (2, "eki", 3, 64, 21, [0, 16, 24, 32, 40, 48, 56, 60, 64]), (3, "aldi", 4, 20, 2, [0, 16, 20]),
+    (2, "aldi", 3, 272, 4300, "library")])
+def test_sharded_host_step_orchestration_matches_single_process(world, rule, d, k, J, bounds):
+    """ces_b200.engine.run_host_phases -- the pipelined host step of a column shard: the means all-reduced chunk by chunk, the
+    own block's D panel accumulated over the chunks with the last chunk deferred behind the start of the gathers -- over
+    gloo with a numpy stand-in for the library pieces: same update as the single-process oracle for 1, 2, 3 and 8 chunks,
+    ragged shards and a rank without particles (J = 2 on 3 ranks); the last case cuts the chunks with the library's own
+    ces_host_chunk_schedule."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_host_worker, args=(r, world, port, rule, d, k, J, bounds, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(240)
+        assert p.exitcode == 0
+    got = sorted(q.get(timeout=10) for _ in range(world))
+    assert len(set(g[4] for g in got)) == 1                      # every rank cut the same number of chunks
+    for rank, err, herr, merr, nchunks, ok_order in got:
+        assert err < 1e-12 and herr < 1e-12 and merr < 1e-12, (rank, err, herr, merr)
+        assert ok_order
+    if bounds == "library":
+        assert got[0][4] > 1
