@@ -98,3 +98,22 @@ def test_host_chunk_schedule_is_rank_independent_and_well_formed():
     assert sched(4096, 65536, 16384, 1)[0] == 3 and sched(4096, 8192, 8192, 8)[0] == 8
     # a measured rate only matters on a single GPU path; the nominal one is used otherwise by the caller
     assert sched(4096, 65536, 16384, 1, 55.0)[0] == 3 and sched(4096, 65536, 16384, 1, 5.0)[0] > 3
+
+
+def test_header_is_plain_c():
+    """include/ces_b200.h is the drop-in boundary for hosts in any language: it must parse as C99 (no C++ types, no torch
+    types in the signatures) and as C++."""
+    import shutil
+    import subprocess
+    import tempfile
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    with tempfile.TemporaryDirectory() as tmp:
+        src = os.path.join(tmp, "h.c")
+        with open(src, "w") as fh:
+            fh.write('#include "ces_b200.h"\nint main(void) { return (int)sizeof(ces_handle_t) * 0; }\n')
+        inc = os.path.join(ROOT, "include")
+        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", inc, "-fsyntax-only", src])
+        if shutil.which("g++"):
+            subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-I", inc, "-fsyntax-only", "-x", "c++", src])

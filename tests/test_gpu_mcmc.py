@@ -90,3 +90,22 @@ def test_model_mh_refuses_what_it_does_not_cover():
         mc.model_mh(Host(), 10, prior, enka, Gamma)
     with pytest.raises(NotImplementedError):
         mc.gp_mh(enka, 10, prior)
+
+
+def test_calibrate_then_sample_example():
+    """examples/linear_ces.py: the reference's Calibrate -> Sample hand-off (linear.ipynb scenario) end to end on the device:
+    sampling.run finds the posterior region, MCMC.model_mh scaled by eks.Ustar samples it; the pooled chains reproduce the
+    analytic posterior (the notebook prints mean [-1.0367 2.0870], cov [[0.01007 0.00034] [0.00034 0.00176]])."""
+    import importlib.util
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("linear_ces_example", os.path.join(root, "examples", "linear_ces.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = mod.main(["--J", "100", "--T", "400", "--n-mcmc", "6000", "--chains", "64"])
+    assert np.allclose(out["posterior_mean"], [-1.03673079, 2.08697021], atol=2e-3)
+    assert np.abs(out["eks_mean"] - out["posterior_mean"]).max() < 0.08              # one ensemble of 100 particles
+    assert np.abs(out["mcmc_mean"] - out["posterior_mean"]).max() < 0.01
+    ratio = np.diag(out["mcmc_cov"]) / np.diag(out["posterior_cov"])
+    assert np.all(np.abs(ratio - 1.0) < 0.15) and 0.05 < out["accept"] < 0.9
+    assert out["mcmc"].samples.shape == (2, 6001) and out["mcmc"].samples_chains.shape == (64, 2, 6001)
