@@ -110,3 +110,69 @@ def test_product_never_imports_the_oracle():
             if name.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, name)).read()
                 assert "import oracle" not in text and "from oracle" not in text, name
+
+
+class _CountingEngine(object):
+    """Stand-in for the device engine: counts how often the problem data is (re-)uploaded."""
+
+    def __init__(self):
+        self.uploads = 0
+
+    def set_problem(self, *arrays):
+        self.uploads += 1
+        self.last = [np.array(a, copy=True) for a in arrays]
+
+
+def test_problem_cache_is_keyed_on_content():
+    """The device copy of (y_obs, Gamma, sigma, mu, ustar) and its factorisations are reused between calls only while the
+    CONTENT of the five arrays is unchanged: in-place edits that a strided checksum would miss (a permutation of y_obs, one
+    entry of a large Gamma) trigger a re-upload; the deferred check of large arrays (run while the GPU step executes) reports
+    the edit afterwards so the caller can repeat the step."""
+    k, p = 400, 3                                   # Gamma: 1.28 MB > the 1 MB threshold of the deferred check
+    rng = np.random.default_rng(0)
+    y, Gamma = rng.standard_normal(k), np.eye(k) * 0.01
+    s = calibrate.sampling(p, k, 10)
+    s.mu, s.sigma, s.ustar = np.zeros((p, 1)), np.eye(p), np.zeros((p, 1))
+    eng = _CountingEngine()
+    assert s._sync_problem(eng, y, Gamma) is None and eng.uploads == 1
+    assert s._sync_problem(eng, y, Gamma) is None and eng.uploads == 1            # unchanged: no upload
+    y[[0, 1]] = y[[1, 0]]                                                         # a permutation keeps every plain sum
+    s._sync_problem(eng, y, Gamma)
+    assert eng.uploads == 2 and np.array_equal(eng.last[0], y)
+    Gamma[123, 77] = Gamma[77, 123] = 1e-4                                        # one entry of a large matrix
+    s._sync_problem(eng, y, Gamma)
+    assert eng.uploads == 3 and eng.last[1][123, 77] == 1e-4
+    s.mu[1, 0] = 0.25                                                             # small arrays: always checked at once
+    s._sync_problem(eng, y, Gamma)
+    assert eng.uploads == 4
+    # deferred mode (the eks_update* path): identical buffers -> the large digest runs in the background
+    stale = s._sync_problem(eng, y, Gamma, defer_large=True)
+    assert eng.uploads == 4 and callable(stale) and stale() is False and eng.uploads == 4
+    Gamma[5, 5] = 0.02                                                            # edited in place, same object
+    stale = s._sync_problem(eng, y, Gamma, defer_large=True)
+    assert eng.uploads == 4                                                       # not seen yet: the step would run on stale data ...
+    assert stale() is True and eng.uploads == 5 and eng.last[1][5, 5] == 0.02     # ... and is reported: the caller repeats it
+    assert s._sync_problem(eng, y, Gamma, defer_large=True)() is False
+    # a new but equal array (different object, same bytes) does not re-upload
+    assert s._sync_problem(eng, y.copy(), Gamma.copy()) is None and eng.uploads == 5
+
+
+def test_reference_arm_of_bench_runs_on_the_host(tmp_path):
+    """bench.py --impl reference needs no GPU: it times the real reference (or the staged copy / the port) on the host and
+    prints one JSON line that names the ensemble size it ran."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, OMP_NUM_THREADS="1")                                   # what torch.distributed.run exports
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "small", "--steps", "2",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=root, env=env)
+    assert out.returncode == 0, out.stderr[-1500:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["value"] > 0 and d["config"]["J_sample"] == d["cpu_baseline"]["J_sample"] == 1024
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
+    assert d["e2e"] == {"value": d["value"], "unit": "particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["steps"] == 2 and d["warmup"] == 0 and d["gpu_launches"] == 0
