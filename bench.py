@@ -907,12 +907,20 @@ def main():
                     line["configs"] = list(configs)
                     PARTIAL["line"] = dict(line)
 
+            def attempt(name, fn):
+                # a failing side configuration must not take the headline line with it (an exception raised on every
+                # rank alike; a rank-local one ends in the deadline guard)
+                try:
+                    add(fn())
+                except Exception as exc:                        # noqa: BLE001
+                    add({"name": name, "error": "%s: %s" % (type(exc).__name__, exc)} if ctx.rank == 0 else None)
+
             if ctx.world == 1:
-                add(cfg1_workload(ctx, with_cpu=cpu))
-                add(brief(darcy_workload(ctx, "cfg2", short, 3, with_cpu=False), "cfg2"))
-            add(brief(update_workload(ctx, "cfg3", short, 3, "interaction", with_cpu=False,
-                                      with_parity=not args.no_parity), "cfg3"))
-            add(brief(darcy_workload(ctx, "cfg4", 2, 3, with_cpu=False), "cfg4"))
+                attempt("cfg1", lambda: cfg1_workload(ctx, with_cpu=cpu))
+                attempt("cfg2", lambda: brief(darcy_workload(ctx, "cfg2", short, 3, with_cpu=False), "cfg2"))
+            attempt("cfg3", lambda: brief(update_workload(ctx, "cfg3", short, 3, "interaction", with_cpu=False,
+                                                          with_parity=not args.no_parity), "cfg3"))
+            attempt("cfg4", lambda: brief(darcy_workload(ctx, "cfg4", 2, 3, with_cpu=False), "cfg4"))
     PARTIAL["done"] = True
     if ctx.rank == 0 and line is not None:
         emit(line)
