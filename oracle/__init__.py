@@ -17,6 +17,11 @@ forward_oracle   numpy restatement of the ``ces.utils`` map-type forward
 darcy_oracle     scipy restatement of ces/darcy.py + utilities/mfiles/*.m.
                  PARITY UNPINNED: the reference needs a MATLAB engine that is
                  not available and stores no Darcy output anywhere.
+mcmc_oracle      numpy restatement of ``MCMC.model_mh`` (ces/sample.py:121-196).  Parity
+                 PINNED: reproduces the golden chains of the real reference
+                 (tests/golden/mcmc_cases.npz; tests/test_oracle_mcmc.py).
+darcy_pcg_oracle / lorenz_oracle   restatements of the device's own solver / RK4 scheme (see
+                 their headers).
 reference_loader loads the real reference from /root/reference when present
                  (never at run time on the GPU box).
 """

@@ -109,3 +109,44 @@ def test_calibrate_then_sample_example():
     ratio = np.diag(out["mcmc_cov"]) / np.diag(out["posterior_cov"])
     assert np.all(np.abs(ratio - 1.0) < 0.15) and 0.05 < out["accept"] < 0.9
     assert out["mcmc"].samples.shape == (2, 6001) and out["mcmc"].samples_chains.shape == (64, 2, 6001)
+
+
+@pytest.mark.parametrize("p,k,kind,update", [(1, 1, "lineal", None), (2, 10, "lineal_log", None), (5, 64, "lineal", "pCN"),
+                                             (32, 7, "lineal", None), (32, 64, "lineal", None), (17, 33, "lineal_log", "pCN"),
+                                             (3, 40, "lineal", None)])
+def test_model_mh_matches_the_oracle_on_fresh_problems(p, k, kind, update):
+    """Device chain against oracle/mcmc_oracle.py (itself pinned to the real reference's chains) on seeded problems the
+    golden file does not hold: the limits of the kernel (p = 32, k = 64), a single parameter / observation, dense Gamma and
+    prior covariance, lineal_log, pCN -- samples, acceptance and the generator state."""
+    from oracle import forward_oracle as fo, mcmc_oracle as mo
+
+    rs = np.random.RandomState(100 * p + k)
+    A = rs.normal(size=(k, p)) / np.sqrt(p) * (0.3 if kind == "lineal_log" else 1.0)
+    truth = 0.3 * rs.normal(size=p)
+    fwd = (lambda th: fo.lineal(A, np.asarray(th).reshape(-1, 1))[:, 0]) if kind == "lineal" else \
+          (lambda th: fo.lineal_log(A, np.asarray(th).reshape(-1, 1))[:, 0])
+    y = fwd(truth) + 0.05 * rs.normal(size=k)
+    Q = rs.normal(size=(k, k))
+    Gamma = 0.01 * (np.eye(k) + 0.3 * Q @ Q.T / k)
+    S = rs.normal(size=(p, p))
+    prior = multivariate_normal(0.1 * rs.normal(size=p) if update is None else np.zeros(p), np.eye(p) + 0.2 * S @ S.T / p)
+    J = 3 * p + 8
+    Ustar = truth[:, None] + 0.05 * rs.normal(size=(p, J))
+    kw = {"delta": 0.6, "enka_scaling": True}
+    if update:
+        kw.update(update=update, beta=0.002)
+    np.random.seed(77)
+    want, want_acc = mo.model_mh(fwd, 200, prior, Ustar, y, Gamma, **kw)
+    state = np.random.get_state()
+    enka = calibrate.sampling(p, k, J)
+    enka.Ustar = Ustar
+    mc = csample.MCMC()
+    mc.y_obs = y
+    model = cutils.lineal(A) if kind == "lineal" else cutils.lineal_log(A)
+    np.random.seed(77)
+    mc.model_mh(model, 200, prior, enka, Gamma, **kw)
+    assert mc.samples.shape == want.shape == (p, 201)
+    assert np.abs(mc.samples - want).max() <= 1e-9 * max(np.abs(want).max(), 1e-300), (p, k, kind, update)
+    assert abs(mc.accept - want_acc) < 1e-12 and 0.0 < want_acc < 1.0
+    got = np.random.get_state()
+    assert np.array_equal(got[1], state[1]) and got[2] == state[2] and got[3] == state[3]
