@@ -176,3 +176,26 @@ def test_reference_arm_of_bench_runs_on_the_host(tmp_path):
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
     assert d["e2e"] == {"value": d["value"], "unit": "particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["steps"] == 2 and d["warmup"] == 0 and d["gpu_launches"] == 0
+
+
+def test_bench_flop_models_agree_with_the_oracle():
+    """bench.py carries its own copies of the flop models (the GPU arm must not import oracle/ for them): W_step of SURVEY.md
+    section 8(d) and the reference-as-written model of BASELINE.md section 3 stay identical to the oracle's."""
+    import importlib.util
+
+    from oracle import eks_oracle as eo
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for (J, d, k) in [(100, 2, 10), (1024, 64, 50), (16384, 1024, 4096), (65536, 1024, 4096)]:
+        for dense in (False, True):
+            assert bench.algorithmic_flops(J, d, k, dense) == eo.algorithmic_flops(J, d, k, dense)
+        assert bench.reference_flops(J, d, k) == eo.reference_flops(J, d, k)
+    assert abs(bench.algorithmic_flops(65536, 1024, 4096) - 4.44e13) < 0.02e13          # the target's W_step (DESIGN section 5)
+    # the workloads bench.py names are BASELINE.json's
+    assert bench.WORKLOADS["target"] == (1024, 4096, 65536) and bench.WORKLOADS["cfg3"] == (1024, 4096, 16384)
+    assert bench.DARCY_WORKLOADS["cfg2"][:4] == (64, 64, 50, 1024) and bench.DARCY_WORKLOADS["cfg4"][:4] == (128, 256, 50, 65536)
+    pr = bench.cfg1_problem()
+    assert pr["U0"].shape == (2, 100) and pr["T"] == 1000 and pr["A"].shape == (10, 2)
